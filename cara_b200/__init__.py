@@ -1,0 +1,2 @@
+"""cara_b200 -- B200-native (sm_100a) implementation of the CaRA fine-tuning hot path."""
+__version__ = "0.1.0"

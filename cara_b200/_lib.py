@@ -1,0 +1,67 @@
+"""ctypes binding of ``libcara_b200.so`` (the C ABI declared in include/cara_b200.h).
+
+The library is the product: there is no CPU / eager fallback.  ``lib()`` raises if the shared object is
+missing or does not export what the header declares.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcara_b200.so")
+
+EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K0", C.c_int),
+        ("A0", C.c_void_p), ("lda0", C.c_long),
+        ("B0", C.c_void_p), ("ldb0", C.c_long),
+        ("K1", C.c_int), ("ext_slices", C.c_int),
+        ("A1", C.c_void_p), ("lda1", C.c_long),
+        ("B1", C.c_void_p), ("ldb1", C.c_long),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int),
+        ("out2", C.c_void_p), ("ldo2", C.c_int),
+        ("aux", C.c_void_p), ("ldaux", C.c_int),
+        ("epi", C.c_int), ("num_sms", C.c_int),
+    ]
+
+
+_SIGS = {
+    "cara_abi_version": (C.c_int, []),
+    "cara_last_error": (C.c_char_p, []),
+    "cara_set_device": (C.c_int, [C.c_int]),
+    "cara_gemm_cp": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+}
+
+_lib = None
+
+
+class CaraLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CaraLibraryError(
+                "libcara_b200.so is not built (%s); run `python -m cara_b200.build` -- there is no fallback path"
+                % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise CaraLibraryError("%s failed: %s" % (what, lib().cara_last_error().decode()))
+
+
+def exported_symbols():
+    return sorted(_SIGS)
