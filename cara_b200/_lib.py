@@ -28,11 +28,27 @@ class GemmDesc(C.Structure):
     ]
 
 
+_P = C.c_void_p
+
 _SIGS = {
     "cara_abi_version": (C.c_int, []),
     "cara_last_error": (C.c_char_p, []),
     "cara_set_device": (C.c_int, [C.c_int]),
     "cara_gemm_cp": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "cara_ln_fwd": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+    "cara_ln_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_adapter_rows_fwd": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "cara_adapter_rows_bwd": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "cara_adapter_cols": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, _P, C.c_long, C.c_int, C.c_int, _P, _P, _P]),
+    "cara_attn_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "cara_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "cara_patchify": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_merge_weights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_adamw_step": (C.c_int, [_P, _P, _P, _P, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_int, C.c_float, _P]),
+    "cara_sgemm": (C.c_int, [_P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P, C.c_int, C.c_int,
+                             C.c_int, C.c_float, C.c_float, _P]),
 }
 
 _lib = None

@@ -1,6 +1,7 @@
 // C-ABI entry points (include/cara_b200.h).  Thin: validate, translate, launch.
 #include "../../include/cara_b200.h"
 #include "gemm_sm100.h"
+#include "kernels.h"
 
 #include <cstdio>
 #include <cstring>
@@ -46,6 +47,79 @@ int cara_gemm_cp(const cara_gemm_desc* d, void* stream) {
   int rc = cara::gemm_cp_launch(g, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(rc, "cara_gemm_cp: launch failed / bad arguments");
   return 0;
+}
+
+#define CARA_STREAM(s) static_cast<cudaStream_t>(s)
+#define CARA_RET(rc, name) do { int rc_ = (rc); return rc_ == 0 ? 0 : fail(rc_, name); } while (0)
+typedef __nv_bfloat16 bf16;
+
+int cara_ln_fwd(const float* x_in, const void* delta, const float* rowscale, int rows_per_sample, float* x_out,
+                const float* gamma, const float* beta, void* h, float* mean, float* rstd, int M, int C, float eps,
+                int act_fp32, void* stream) {
+  cara::LnFwdArgs a{x_in, delta, rowscale, rows_per_sample > 0 ? rows_per_sample : 1, x_out, gamma, beta, h, mean,
+                    rstd, M, C, eps, act_fp32};
+  CARA_RET(cara::ln_fwd_launch(a, CARA_STREAM(stream)), "cara_ln_fwd");
+}
+int cara_ln_bwd(const void* dh, const float* x, const float* mean, const float* rstd, const float* gamma,
+                const float* dx_in, float* dx_out, void* g_out, const float* rowscale, int rows_per_sample, int M,
+                int C, int act_fp32, void* stream) {
+  cara::LnBwdArgs a{dh, x, mean, rstd, gamma, dx_in, dx_out, g_out, rowscale,
+                    rows_per_sample > 0 ? rows_per_sample : 1, M, C, act_fp32};
+  CARA_RET(cara::ln_bwd_launch(a, CARA_STREAM(stream)), "cara_ln_bwd");
+}
+int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At, const float* scales, int slices,
+                          int Rp, float* T, void* Uhat, void* stream) {
+  cara::RowsArgs a{};
+  a.X = static_cast<const bf16*>(X); a.ldx = ldx; a.M = M; a.kslice = K;
+  a.Ft = static_cast<const bf16*>(At); a.ldf = K; a.scales = scales; a.mode = 0; a.s_out = slices;
+  a.T = T; a.U = static_cast<bf16*>(Uhat); a.ldu = static_cast<long>(slices) * Rp; a.dc = nullptr;
+  CARA_RET(cara::rows_launch(a, Rp, 1, CARA_STREAM(stream)), "cara_adapter_rows_fwd");
+}
+int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int slices, const void* Bt, const float* scales,
+                          int Rp, const float* T, void* dThat, float* dscales, void* stream) {
+  if (slices < 1 || N % slices != 0) return fail(-30, "cara_adapter_rows_bwd: bad slices");
+  cara::RowsArgs a{};
+  a.X = static_cast<const bf16*>(G); a.ldx = ldg; a.M = M; a.kslice = N / slices;
+  a.Ft = static_cast<const bf16*>(Bt); a.ldf = N / slices; a.scales = scales; a.mode = 1; a.s_out = 0;
+  a.T = const_cast<float*>(T); a.U = static_cast<bf16*>(dThat); a.ldu = Rp; a.dc = dscales;
+  CARA_RET(cara::rows_launch(a, Rp, slices, CARA_STREAM(stream)), "cara_adapter_rows_bwd");
+}
+int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, long ldv, int slices, int Rp, float* out,
+                      float* colsum, void* stream) {
+  if (slices < 1 || Kc % slices != 0) return fail(-40, "cara_adapter_cols: bad slices");
+  cara::ColsArgs a{};
+  a.X = static_cast<const bf16*>(X); a.ldx = ldx; a.M = M; a.Kc = Kc;
+  a.V = static_cast<const bf16*>(V); a.ldv = ldv; a.slice_w = Kc / slices; a.out = out; a.colsum = colsum;
+  CARA_RET(cara::cols_launch(a, Rp, 0, CARA_STREAM(stream)), "cara_adapter_cols");
+}
+int cara_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int D, float scale, void* stream) {
+  cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(o), lse, nullptr, nullptr, B, N, H, D, scale};
+  CARA_RET(cara::attn_fwd_launch(a, CARA_STREAM(stream)), "cara_attn_fwd");
+}
+int cara_attn_bwd(const void* qkv, const void* o, const float* lse, const void* d_o, void* dqkv, int B, int N, int H,
+                  int D, float scale, void* stream) {
+  cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(const_cast<void*>(o)), const_cast<float*>(lse),
+                   static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), B, N, H, D, scale};
+  CARA_RET(cara::attn_bwd_launch(a, CARA_STREAM(stream)), "cara_attn_bwd");
+}
+int cara_patchify(const float* img, void* patches, int B, int Cin, int S, int P, int Kp, void* stream) {
+  CARA_RET(cara::patchify_launch(img, static_cast<bf16*>(patches), B, Cin, S, P, Kp, CARA_STREAM(stream)), "cara_patchify");
+}
+int cara_assemble_tokens(const void* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
+                         void* stream) {
+  CARA_RET(cara::assemble_launch(static_cast<const bf16*>(pe), cls, pos, x, B, N, C, CARA_STREAM(stream)), "cara_assemble_tokens");
+}
+int cara_merge_weights(const float* W, const float* A, const float* Bf, const float* cs, void* Weff, int N, int K,
+                       int slices, int R, void* stream) {
+  CARA_RET(cara::merge_launch(W, A, Bf, cs, static_cast<bf16*>(Weff), N, K, slices, R, CARA_STREAM(stream)), "cara_merge_weights");
+}
+int cara_adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float gscale, void* stream) {
+  CARA_RET(cara::adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale, CARA_STREAM(stream)), "cara_adamw_step");
+}
+int cara_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
+               const float* bias, int M, int N, int K, float alpha, float beta, void* stream) {
+  CARA_RET(cara::sgemm_launch(A, ars, acs, B, brs, bcs, C, ldc, bias, M, N, K, alpha, beta, CARA_STREAM(stream)), "cara_sgemm");
 }
 
 }  // extern "C"

@@ -1,0 +1,64 @@
+// Internal launch interfaces of the non-GEMM kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace cara {
+
+struct LnFwdArgs {
+  const float* x_in; const void* delta; const float* rowscale; int rows_per_sample;
+  float* x_out; const float* gamma; const float* beta; void* h; float* mean; float* rstd;
+  int M, C; float eps; int act_fp32;
+};
+struct LnBwdArgs {
+  const void* dh; const float* x; const float* mean; const float* rstd; const float* gamma;
+  const float* dx_in; float* dx_out; void* g_out; const float* rowscale; int rows_per_sample;
+  int M, C; int act_fp32;
+};
+int ln_fwd_launch(const LnFwdArgs& a, cudaStream_t st);
+int ln_bwd_launch(const LnBwdArgs& a, cudaStream_t st);
+
+// Tall-skinny adapter contractions (skinny.cu)
+struct RowsArgs {
+  const __nv_bfloat16* X; long ldx; int M; int kslice;  // X [M, CS*kslice]
+  const __nv_bfloat16* Ft; long ldf;                     // factor transposed [Rp, kslice]
+  const float* scales;                                   // fwd [s_out, Rp] / bwd [CS, Rp]
+  int mode;                                              // 0 fwd, 1 bwd
+  int s_out;
+  float* T;                                              // [M, Rp] fp32 (fwd: out, bwd: in)
+  __nv_bfloat16* U; long ldu;                            // fwd Uhat [M, s_out*Rp] / bwd dThat [M, Rp]
+  float* dc;                                             // bwd [CS, Rp], atomically accumulated
+};
+int rows_launch(const RowsArgs& a, int rp, int cs, cudaStream_t st);
+
+struct ColsArgs {
+  const __nv_bfloat16* X; long ldx; int M; int Kc;      // X [M, Kc]
+  const __nv_bfloat16* V; long ldv;                      // V [M, (Kc/slice_w)*Rp]
+  int slice_w;
+  float* out;                                            // [slice_w, Rp] fp32, accumulated
+  float* colsum;                                         // [Kc] fp32 or null, accumulated
+  int rows_per_cta;
+};
+int cols_launch(const ColsArgs& a, int rp, int num_sms, cudaStream_t st);
+
+// Attention core (attention.cu): qkv [B, N, 3, H, D] -> o [B, N, H, D]
+struct AttnArgs {
+  const __nv_bfloat16* qkv; __nv_bfloat16* o; float* lse;       // lse [B, H, N] (log2 domain)
+  const __nv_bfloat16* d_o; __nv_bfloat16* dqkv;                // backward only
+  int B, N, H, D; float scale;
+};
+int attn_fwd_launch(const AttnArgs& a, cudaStream_t st);
+int attn_bwd_launch(const AttnArgs& a, cudaStream_t st);
+
+// misc.cu
+int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S, int P, int Kp, cudaStream_t st);
+int assemble_launch(const __nv_bfloat16* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
+                    cudaStream_t st);
+int merge_launch(const float* W, const float* A, const float* Bf, const float* cs, __nv_bfloat16* out, int N, int K,
+                 int slices, int R, cudaStream_t st);
+int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                 float wd, int step, float gscale, cudaStream_t st);
+int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
+                 const float* bias, int M, int N, int K, float alpha, float beta, cudaStream_t st);
+
+}  // namespace cara

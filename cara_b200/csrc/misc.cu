@@ -1,0 +1,192 @@
+// Small kernels around the hot path: patch embedding staging (timm PatchEmbed as an im2col + GEMM),
+// token assembly (cls token + position embedding), eval-mode merge of the CP delta into the frozen
+// weights, fused AdamW over one flat fp32 buffer (vit_cp.py:185), and a plain fp32 SIMT
+// GEMM for the tiny trainable head (vit_cp.py:166).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace cara {
+
+// ---------------------------------------------------------------- patchify (im2col for conv PxP / stride P)
+// img fp32 [B, Cin, S, S] -> patches bf16 [B*np, Kp], column = (c, py, px), zero padded to Kp.
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Cin,
+                                int S, int P, int Kp) {
+  const int gp = S / P;
+  const long rows = static_cast<long>(B) * gp * gp;
+  const int segs = Cin * P;                       // (c, py) segments of P contiguous pixels
+  const long total = rows * (segs + 1);           // +1: the zero padding segment
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = i / (segs + 1);
+    const int seg = static_cast<int>(i % (segs + 1));
+    __nv_bfloat16* o = out + row * Kp;
+    if (seg == segs) {
+      for (int k = segs * P; k < Kp; ++k) o[k] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    const int b = static_cast<int>(row / (gp * gp)), pi = static_cast<int>(row % (gp * gp));
+    const int py0 = (pi / gp) * P, px0 = (pi % gp) * P;
+    const int c = seg / P, py = seg % P;
+    const float* src = img + ((static_cast<long>(b) * Cin + c) * S + (py0 + py)) * S + px0;
+    for (int px = 0; px < P; ++px) o[seg * P + px] = __float2bfloat16_rn(src[px]);
+  }
+}
+
+// x[b, 0, :] = cls + pos[0];  x[b, 1+p, :] = pe[b*np + p, :] + pos[1+p]   (fp32 residual stream)
+__global__ void assemble_kernel(const __nv_bfloat16* __restrict__ pe, const float* __restrict__ cls,
+                                const float* __restrict__ pos, float* __restrict__ x, int B, int N, int C) {
+  const long total = static_cast<long>(B) * N * (C / 4);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % (C / 4));
+    const long tok = i / (C / 4);
+    const int n = static_cast<int>(tok % N), b = static_cast<int>(tok / N);
+    const float4 p = *reinterpret_cast<const float4*>(pos + static_cast<long>(n) * C + c4 * 4);
+    float4 v;
+    if (n == 0) {
+      v = *reinterpret_cast<const float4*>(cls + c4 * 4);
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(pe + (static_cast<long>(b) * (N - 1) + (n - 1)) * C + c4 * 4);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v = make_float4(a.x, a.y, d.x, d.y);
+    }
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    *reinterpret_cast<float4*>(x + tok * C + c4 * 4) = v;
+  }
+}
+
+int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S, int P, int Kp, cudaStream_t st) {
+  if (S % P != 0 || Kp < Cin * P * P) return -60;
+  patchify_kernel<<<148 * 8, 256, 0, st>>>(img, out, B, Cin, S, P, Kp);
+  return cudaGetLastError() == cudaSuccess ? 0 : -61;
+}
+int assemble_launch(const __nv_bfloat16* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
+                    cudaStream_t st) {
+  if (C % 4 != 0) return -62;
+  assemble_kernel<<<148 * 8, 256, 0, st>>>(pe, cls, pos, x, B, N, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : -63;
+}
+
+// ---------------------------------------------------------------- eval-mode merge
+// Weff[n, k] = W[n, k] + sum_r (Bf[n mod w, r] * cs[n / w, r]) * A[k, r]      W fp32 -> Weff bf16
+template <int R>
+__global__ void __launch_bounds__(128)
+merge_kernel(const float* __restrict__ W, const float* __restrict__ A, const float* __restrict__ Bf,
+             const float* __restrict__ cs, __nv_bfloat16* __restrict__ out, int N, int K, int w) {
+  __shared__ float bc[8][R];
+  const int n0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 8 * R; i += 128) {
+    const int n = n0 + i / R, r = i % R;
+    bc[i / R][r] = n < N ? Bf[static_cast<long>(n % w) * R + r] * cs[(n / w) * R + r] : 0.f;
+  }
+  __syncthreads();
+  const int k = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (k >= K) return;
+  float a0[R], a1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { a0[r] = A[static_cast<long>(k) * R + r]; a1[r] = A[static_cast<long>(k + 1) * R + r]; }
+  for (int i = 0; i < 8 && n0 + i < N; ++i) {
+    const float2 wv = *reinterpret_cast<const float2*>(W + static_cast<long>(n0 + i) * K + k);
+    float d0 = wv.x, d1 = wv.y;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { d0 = fmaf(bc[i][r], a0[r], d0); d1 = fmaf(bc[i][r], a1[r], d1); }
+    *reinterpret_cast<__nv_bfloat162*>(out + static_cast<long>(n0 + i) * K + k) = __floats2bfloat162_rn(d0, d1);
+  }
+}
+
+int merge_launch(const float* W, const float* A, const float* Bf, const float* cs, __nv_bfloat16* out, int N, int K,
+                 int slices, int R, cudaStream_t st) {
+  if (K % 2 != 0 || slices < 1 || N % slices != 0) return -64;
+  const dim3 grid((K / 2 + 127) / 128, (N + 7) / 8);
+  const int w = N / slices;
+  switch (R) {
+    case 4: merge_kernel<4><<<grid, 128, 0, st>>>(W, A, Bf, cs, out, N, K, w); break;
+    case 8: merge_kernel<8><<<grid, 128, 0, st>>>(W, A, Bf, cs, out, N, K, w); break;
+    case 16: merge_kernel<16><<<grid, 128, 0, st>>>(W, A, Bf, cs, out, N, K, w); break;
+    case 32: merge_kernel<32><<<grid, 128, 0, st>>>(W, A, Bf, cs, out, N, K, w); break;
+    default: return -65;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -66;
+}
+
+// ---------------------------------------------------------------- fused AdamW (torch.optim.AdamW semantics)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, float gscale) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * mi / denom;
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                 float wd, int step, float gscale, cudaStream_t st) {
+  if (n <= 0 || step < 1) return -67;
+  const float bc1 = 1.0f - powf(b1, static_cast<float>(step));
+  const float bc2s = sqrtf(1.0f - powf(b2, static_cast<float>(step)));
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  adamw_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, gscale);
+  return cudaGetLastError() == cudaSuccess ? 0 : -68;
+}
+
+// ---------------------------------------------------------------- fp32 SIMT GEMM with general strides
+// C[m,n] = alpha * sum_k A(m,k) B(k,n) + beta * C[m,n] + bias[n];  A(m,k) = A[m*ars + k*acs], B(k,n) = B[k*brs + n*bcs]
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, long ars, long acs, const float* __restrict__ B, long brs, long bcs,
+             float* __restrict__ C, long ldc, const float* __restrict__ bias, int M, int N, int K, float alpha,
+             float beta) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int kk = i & 15, r = i >> 4;
+      As[kk][r] = (m0 + r < M && k0 + kk < K) ? A[(m0 + r) * ars + (k0 + kk) * acs] : 0.f;
+      Bs[kk][r] = (n0 + r < N && k0 + kk < K) ? B[(k0 + kk) * brs + (n0 + r) * bcs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (bias != nullptr) v += bias[n];
+      if (beta != 0.f) v += beta * C[m * ldc + n];
+      C[m * ldc + n] = v;
+    }
+  }
+}
+int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
+                 const float* bias, int M, int N, int K, float alpha, float beta, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return -69;
+  sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, ars, acs, B, brs, bcs, C, ldc, bias, M, N, K,
+                                                                   alpha, beta);
+  return cudaGetLastError() == cudaSuccess ? 0 : -70;
+}
+
+}  // namespace cara

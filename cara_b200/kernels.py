@@ -1,0 +1,206 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/cara_b200.h).
+
+PyTorch owns the memory and the stream; these functions only pass ``data_ptr()``s, sizes and
+``torch.cuda.current_stream()`` through ctypes.  Every function requires CUDA tensors: there is no CPU
+path here by design.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+launch_count = 0  # number of cara_* kernel launches issued (bench.py reports it as gpu_launches)
+_dev = [None]
+
+
+def _prep(t):
+    global launch_count
+    if not t.is_cuda:
+        raise L.CaraLibraryError("cara_b200 kernels need CUDA tensors (no CPU fallback)")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if _dev[0] != idx:
+        L.check(L.lib().cara_set_device(idx), "cara_set_device")
+        _dev[0] = idx
+    launch_count += 1
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def round_rank(r):
+    return 16 if r <= 16 else 32
+
+
+def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, out=None, out2=None, aux=None,
+            want_pre=True, num_sms=0):
+    """out[M,N] = a0[M,K0] b0[N,K0]^T + bias (+ adapter segment a1/b1), see cara_gemm_cp."""
+    st = _prep(a0)
+    M, K0 = a0.shape
+    N = b0.shape[0]
+    assert a0.dtype == BF16 and b0.dtype == BF16 and b0.shape[1] == K0
+    assert a0.stride(1) == 1 and b0.stride(1) == 1
+    d = L.GemmDesc()
+    d.M, d.N, d.K0 = M, N, K0
+    d.A0, d.lda0, d.B0, d.ldb0 = a0.data_ptr(), a0.stride(0), b0.data_ptr(), b0.stride(0)
+    if a1 is not None:
+        K1 = b1.shape[1]
+        assert a1.dtype == BF16 and b1.dtype == BF16 and a1.shape == (M, ext_slices * K1)
+        assert b1.shape[0] * ext_slices == N and a1.stride(1) == 1 and b1.stride(1) == 1
+        d.K1, d.ext_slices = K1, ext_slices
+        d.A1, d.lda1, d.B1, d.ldb1 = a1.data_ptr(), a1.stride(0), b1.data_ptr(), b1.stride(0)
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
+        d.bias = bias.data_ptr()
+    if out is None and (epi != L.EPI_GELU or want_pre):
+        out = torch.empty((M, N), device=a0.device, dtype=BF16)
+    if out is not None:
+        d.out, d.ldo = out.data_ptr(), out.stride(0)
+    if epi == L.EPI_GELU:
+        if out2 is None:
+            out2 = torch.empty((M, N), device=a0.device, dtype=BF16)
+        d.out2, d.ldo2 = out2.data_ptr(), out2.stride(0)
+    if epi == L.EPI_DGELU:
+        assert aux is not None and aux.dtype == BF16 and aux.shape == (M, N)
+        d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
+    d.epi, d.num_sms = epi, num_sms
+    L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
+    return (out, out2) if epi == L.EPI_GELU else out
+
+
+def ln_fwd(x, gamma, beta, delta=None, rowscale=None, rows_per_sample=1, eps=1e-6, act_dtype=BF16,
+           write_x=True, want_stats=True):
+    """Returns (x_out, h, mean, rstd).  x fp32 [M,C]; x_out aliases x when delta is None."""
+    st = _prep(x)
+    M, Cc = x.shape
+    assert x.dtype == F32 and x.is_contiguous()
+    if delta is not None:
+        assert delta.shape == x.shape and delta.dtype == act_dtype and delta.is_contiguous()
+    x_out = torch.empty_like(x) if (delta is not None and write_x) else (x if delta is None else None)
+    h = torch.empty((M, Cc), device=x.device, dtype=act_dtype)
+    mean = torch.empty(M, device=x.device, dtype=F32) if want_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=F32) if want_stats else None
+    L.check(L.lib().cara_ln_fwd(x.data_ptr(), _p(delta), _p(rowscale), rows_per_sample,
+                                _p(x_out) if delta is not None else None, gamma.data_ptr(), beta.data_ptr(),
+                                h.data_ptr(), _p(mean), _p(rstd), M, Cc, eps, int(act_dtype == F32), st), "cara_ln_fwd")
+    return x_out, h, mean, rstd
+
+
+def ln_bwd(dh, x, mean, rstd, gamma, dx_in=None, rowscale=None, rows_per_sample=1, want_g=False):
+    """Returns (dx_out fp32, g_out or None)."""
+    st = _prep(x)
+    M, Cc = x.shape
+    dx_out = torch.empty_like(x)
+    g_out = torch.empty((M, Cc), device=x.device, dtype=dh.dtype) if want_g else None
+    L.check(L.lib().cara_ln_bwd(dh.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                _p(dx_in), dx_out.data_ptr(), _p(g_out), _p(rowscale), rows_per_sample, M, Cc,
+                                int(dh.dtype == F32), st), "cara_ln_bwd")
+    return dx_out, g_out
+
+
+def adapter_rows_fwd(x, a_t, scales):
+    """x bf16 [M,K]; a_t bf16 [Rp,K]; scales fp32 [S,Rp] -> (T fp32 [M,Rp], Uhat bf16 [M,S*Rp])."""
+    st = _prep(x)
+    M, K = x.shape
+    Rp = a_t.shape[0]
+    S = scales.shape[0]
+    assert a_t.shape == (Rp, K) and a_t.is_contiguous() and scales.shape == (S, Rp) and scales.is_contiguous()
+    T = torch.empty((M, Rp), device=x.device, dtype=F32)
+    U = torch.empty((M, S * Rp), device=x.device, dtype=BF16)
+    L.check(L.lib().cara_adapter_rows_fwd(x.data_ptr(), x.stride(0), M, K, a_t.data_ptr(), scales.data_ptr(), S, Rp,
+                                          T.data_ptr(), U.data_ptr(), st), "cara_adapter_rows_fwd")
+    return T, U
+
+
+def adapter_rows_bwd(g, b_t, scales, T):
+    """g bf16 [M,N]; b_t bf16 [Rp,N/S]; scales [S,Rp]; T fp32 [M,Rp] -> (dThat bf16 [M,Rp], dscales fp32 [S,Rp])."""
+    st = _prep(g)
+    M, N = g.shape
+    S, Rp = scales.shape
+    assert b_t.shape == (Rp, N // S) and b_t.is_contiguous() and T.shape == (M, Rp)
+    dT = torch.empty((M, Rp), device=g.device, dtype=BF16)
+    dsc = torch.zeros((S, Rp), device=g.device, dtype=F32)
+    L.check(L.lib().cara_adapter_rows_bwd(g.data_ptr(), g.stride(0), M, N, S, b_t.data_ptr(), scales.data_ptr(), Rp,
+                                          T.data_ptr(), dT.data_ptr(), dsc.data_ptr(), st), "cara_adapter_rows_bwd")
+    return dT, dsc
+
+
+def adapter_cols(x, v, slices, Rp, want_colsum=False):
+    """out [Kc/slices, Rp] = sum_s x[:, slice s]^T v[:, s*Rp:+Rp]; colsum [Kc] = column sums of x."""
+    st = _prep(x)
+    M, Kc = x.shape
+    assert v.shape == (M, slices * Rp) and x.stride(1) == 1 and v.stride(1) == 1
+    out = torch.zeros((Kc // slices, Rp), device=x.device, dtype=F32)
+    cs = torch.zeros(Kc, device=x.device, dtype=F32) if want_colsum else None
+    L.check(L.lib().cara_adapter_cols(x.data_ptr(), x.stride(0), M, Kc, v.data_ptr(), v.stride(0), slices, Rp,
+                                      out.data_ptr(), _p(cs), st), "cara_adapter_cols")
+    return out, cs
+
+
+def attn_fwd(qkv, B, N, H, D, scale, want_lse=True):
+    st = _prep(qkv)
+    assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.numel() == B * N * 3 * H * D
+    o = torch.empty((B * N, H * D), device=qkv.device, dtype=BF16)
+    lse = torch.empty((B, H, N), device=qkv.device, dtype=F32) if want_lse else None
+    L.check(L.lib().cara_attn_fwd(qkv.data_ptr(), o.data_ptr(), _p(lse), B, N, H, D, scale, st), "cara_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(qkv, o, lse, d_o, B, N, H, D, scale):
+    st = _prep(qkv)
+    assert d_o.is_contiguous() and d_o.dtype == BF16
+    dqkv = torch.empty_like(qkv)
+    L.check(L.lib().cara_attn_bwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(), dqkv.data_ptr(),
+                                  B, N, H, D, scale, st), "cara_attn_bwd")
+    return dqkv
+
+
+def patchify(img, P, Kp):
+    st = _prep(img)
+    B, Cin, S, _ = img.shape
+    assert img.dtype == F32 and img.is_contiguous()
+    out = torch.empty((B * (S // P) ** 2, Kp), device=img.device, dtype=BF16)
+    L.check(L.lib().cara_patchify(img.data_ptr(), out.data_ptr(), B, Cin, S, P, Kp, st), "cara_patchify")
+    return out
+
+
+def assemble_tokens(pe, cls, pos, B, N, Cc):
+    st = _prep(pe)
+    x = torch.empty((B * N, Cc), device=pe.device, dtype=F32)
+    L.check(L.lib().cara_assemble_tokens(pe.data_ptr(), cls.data_ptr(), pos.data_ptr(), x.data_ptr(), B, N, Cc, st),
+            "cara_assemble_tokens")
+    return x
+
+
+def merge_weights(W, A, Bf, cs):
+    """W fp32 [N,K], A fp32 [K,R], Bf fp32 [N/S,R], cs fp32 [S,R] -> bf16 [N,K]."""
+    st = _prep(W)
+    N, K = W.shape
+    S, R = cs.shape
+    out = torch.empty((N, K), device=W.device, dtype=BF16)
+    L.check(L.lib().cara_merge_weights(W.data_ptr(), A.contiguous().data_ptr(), Bf.contiguous().data_ptr(),
+                                       cs.contiguous().data_ptr(), out.data_ptr(), N, K, S, R, st), "cara_merge_weights")
+    return out
+
+
+def adamw_step(p, g, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, gscale=1.0):
+    st = _prep(p)
+    assert p.dtype == F32 and p.is_contiguous() and g.is_contiguous()
+    L.check(L.lib().cara_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0],
+                                    betas[1], eps, weight_decay, step, gscale, st), "cara_adamw_step")
+
+
+def sgemm(A, B, bias=None, out=None, alpha=1.0, beta=0.0):
+    """fp32 C = alpha * A @ B + beta * C + bias for arbitrary-stride 2-D views."""
+    st = _prep(A)
+    M, K = A.shape
+    N = B.shape[1]
+    assert A.dtype == F32 and B.dtype == F32 and B.shape[0] == K
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=F32)
+    L.check(L.lib().cara_sgemm(A.data_ptr(), A.stride(0), A.stride(1), B.data_ptr(), B.stride(0), B.stride(1),
+                               out.data_ptr(), out.stride(0), _p(bias), M, N, K, alpha, beta, st), "cara_sgemm")
+    return out

@@ -54,6 +54,65 @@ typedef struct cara_gemm_desc {
 } cara_gemm_desc;
 CARA_API int cara_gemm_cp(const cara_gemm_desc* d, void* stream);
 
+/* LayerNorm of timm Block.norm1/norm2/norm (eps 1e-6) fused with the residual stream (replaces the
+ * ATen native_layer_norm + add/DropPath kernels of SURVEY 2.1 rows a, m).
+ *   x_out = x_in + rowscale[row / rows_per_sample] * delta   (delta NULL: plain LN of x_in)
+ *   h = LN(x_out) * gamma + beta;  mean/rstd [M] saved for backward.  x is fp32 [M,C]; delta/h are
+ *   bf16 (act_fp32 = 0) or fp32 (act_fp32 = 1).  C must be a multiple of 128. */
+CARA_API int cara_ln_fwd(const float* x_in, const void* delta, const float* rowscale, int rows_per_sample,
+                         float* x_out, const float* gamma, const float* beta, void* h, float* mean, float* rstd,
+                         int M, int C, float eps, int act_fp32, void* stream);
+/* dx_out = dx_in + dLN(dh) (gamma/beta frozen);  g_out (optional) = rowscale * dx_out in the activation
+ * dtype: the incoming gradient of the branch that fed this residual position. */
+CARA_API int cara_ln_bwd(const void* dh, const float* x, const float* mean, const float* rstd, const float* gamma,
+                         const float* dx_in, float* dx_out, void* g_out, const float* rowscale, int rows_per_sample,
+                         int M, int C, int act_fp32, void* stream);
+
+/* Rank-R side chain, forward:  T = X A (fp32 [M,Rp]);  Uhat[:, s*Rp:(s+1)*Rp] = scales[s] (.) T.
+ * X bf16 [M,K]; At = A^T bf16 [Rp,K] (rank zero-padded to Rp in {16,32}); scales fp32 [slices,Rp]. */
+CARA_API int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At, const float* scales,
+                                   int slices, int Rp, float* T, void* Uhat, void* stream);
+/* Backward of the same chain: per output slice s, dU_s = G[:, s*w:(s+1)*w] B;
+ *   dThat = sum_s scales[s] (.) dU_s  (bf16 [M,Rp]);  dscales[s] += sum_m dU_s (.) T  (fp32, accumulated).
+ * G bf16 [M,N]; Bt = B^T bf16 [Rp, N/slices]. */
+CARA_API int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int slices, const void* Bt,
+                                   const float* scales, int Rp, const float* T, void* dThat, float* dscales,
+                                   void* stream);
+/* Factor gradients as skinny contractions over the M tokens (no dW is formed):
+ *   out[k mod w, :] += sum_m X[m,k] V[m, (k/w)*Rp : +Rp]   (w = Kc/slices);  colsum[k] += sum_m X[m,k].
+ * X bf16 [M,Kc] (Kc % 256 == 0), V bf16 [M, slices*Rp]; out fp32 [w,Rp] and colsum fp32 [Kc] are
+ * accumulated into (caller zeroes them). */
+CARA_API int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, long ldv, int slices, int Rp,
+                               float* out, float* colsum, void* stream);
+
+/* Attention core (cara.py:44-48) on the fused projection's [B,N,3,H,D] bf16 output; o is [B,N,H,D];
+ * lse [B,H,N] fp32 (base-2 log-sum-exp of the scaled scores) is saved for backward.  D in {64,80}. */
+CARA_API int cara_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int D, float scale,
+                           void* stream);
+CARA_API int cara_attn_bwd(const void* qkv, const void* o, const float* lse, const void* d_o, void* dqkv, int B,
+                           int N, int H, int D, float scale, void* stream);
+
+/* timm PatchEmbed (conv PxP stride P) as im2col: img fp32 [B,Cin,S,S] -> bf16 [B*(S/P)^2, Kp] (zero padded),
+ * then cara_gemm_cp against the flattened conv weight, then token assembly with cls/pos into the fp32
+ * residual stream x [B,N,C]. */
+CARA_API int cara_patchify(const float* img, void* patches, int B, int Cin, int S, int P, int Kp, void* stream);
+CARA_API int cara_assemble_tokens(const void* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
+                                  void* stream);
+
+/* Eval-mode merge (the reference re-materialises the delta every forward, cara.py:27,52,76,88):
+ *   Weff[n,k] = W[n,k] + sum_r Bf[n mod w, r] cs[n / w, r] A[k, r],  W fp32 [N,K] -> Weff bf16 [N,K]. */
+CARA_API int cara_merge_weights(const float* W, const float* A, const float* Bf, const float* cs, void* Weff, int N,
+                                int K, int slices, int R, void* stream);
+
+/* torch.optim.AdamW update (vit_cp.py:185) over one flat fp32 buffer; grads are pre-multiplied by gscale. */
+CARA_API int cara_adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, float gscale, void* stream);
+
+/* Plain fp32 GEMM with general strides for the tiny trainable head (vit_cp.py:166):
+ *   C[m,n] = alpha * sum_k A[m*ars + k*acs] * B[k*brs + n*bcs] + beta * C[m,n] + bias[n]. */
+CARA_API int cara_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
+                        const float* bias, int M, int N, int K, float alpha, float beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

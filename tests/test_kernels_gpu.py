@@ -1,0 +1,222 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against a plain fp32 torch statement of the same op
+on the same seeded inputs.  bf16 kernels: tolerance is the bf16 rounding of inputs/outputs (rel L2 <= 6e-3);
+fp32 kernels: <= 1e-5.  Full-model parity against the CPU oracle lives in test_parity_gpu.py."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def rel(a, b):
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def K():
+    from cara_b200 import kernels
+    return kernels
+
+
+def _gemm_case(K, M, N, K0, K1=0, S=1, bias=False, epi=0, seed=0):
+    from cara_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a0 = (torch.randn(M, K0, device="cuda", generator=g) * 0.5).to(BF16)
+    b0 = (torch.randn(N, K0, device="cuda", generator=g) * 0.05).to(BF16)
+    ref = a0.float() @ b0.float().T
+    a1 = b1 = bv = aux = None
+    if K1:
+        a1 = (torch.randn(M, S * K1, device="cuda", generator=g) * 0.3).to(BF16)
+        b1 = (torch.randn(N // S, K1, device="cuda", generator=g) * 0.3).to(BF16)
+        w = N // S
+        for s in range(S):
+            ref[:, s * w:(s + 1) * w] += a1[:, s * K1:(s + 1) * K1].float() @ b1.float().T
+    if bias:
+        bv = torch.randn(N, device="cuda", generator=g)
+        ref += bv
+    if epi == L.EPI_DGELU:
+        aux = torch.randn(M, N, device="cuda", generator=g).to(BF16)
+        u = aux.float().requires_grad_(True)
+        torch.nn.functional.gelu(u).sum().backward()
+        ref = ref * u.grad
+    out = K.gemm_cp(a0, b0, bias=bv, a1=a1, b1=b1, ext_slices=S, epi=epi, aux=aux)
+    if epi == L.EPI_GELU:
+        pre, act = out
+        assert rel(pre.float(), ref) < 6e-3
+        assert rel(act.float(), torch.nn.functional.gelu(pre.float())) < 6e-3
+    else:
+        assert rel(out.float(), ref) < 6e-3
+        assert not torch.isnan(out.float()).any()
+
+
+@pytest.mark.parametrize("shape", [
+    (128, 256, 64), (128, 256, 768), (591, 768, 768), (1000, 1024, 1024), (257 * 3, 1280, 1280), (4096, 768, 640)])
+def test_gemm_plain(K, shape):
+    _gemm_case(K, *shape, bias=True)
+
+
+@pytest.mark.parametrize("M,N,K0,K1,S", [
+    (1024, 2304, 768, 16, 3), (1024, 3072, 768, 32, 4), (777, 768, 3072, 16, 1), (394, 3072, 1024, 32, 3),
+    (512, 768, 768, 16, 1)])
+def test_gemm_adapter_segment(K, M, N, K0, K1, S):
+    _gemm_case(K, M, N, K0, K1, S, bias=True)
+
+
+def test_gemm_epilogues(K):
+    from cara_b200 import _lib as L
+    _gemm_case(K, 640, 3072, 768, 16, 4, bias=True, epi=L.EPI_GELU)
+    _gemm_case(K, 640, 3072, 768, 16, 1, epi=L.EPI_DGELU)
+
+
+def test_gemm_full_size_linearity(K):
+    """c2 size (M = 256*197): linearity f(a+b) = f(a) + f(b) up to bf16 output rounding, and a row checksum."""
+    M, N, K0 = 50432, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = (torch.randn(M, K0, device="cuda", generator=g)).to(BF16)
+    w = (torch.randn(N, K0, device="cuda", generator=g) * 0.03).to(BF16)
+    y = K.gemm_cp(a, w).float()
+    ref_rowsum = a.float() @ w.float().sum(0)
+    assert rel(y.sum(1), ref_rowsum) < 2e-3
+    idx = torch.randint(0, M, (512,), device="cuda", generator=g)
+    assert rel(y[idx], a[idx].float() @ w.float().T) < 6e-3
+
+
+@pytest.mark.parametrize("C,act", [(768, BF16), (1024, BF16), (1280, BF16), (256, torch.float32), (768, torch.float32)])
+def test_layernorm_fwd_bwd(K, C, act):
+    M, rps = 197 * 3 + 5, 197
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(M, C, device="cuda", generator=g) * 2 + 0.3
+    delta = torch.randn(M, C, device="cuda", generator=g).to(act)
+    rs = torch.rand((M + rps - 1) // rps, device="cuda", generator=g) + 0.5
+    gamma = torch.randn(C, device="cuda", generator=g) * 0.1 + 1
+    beta = torch.randn(C, device="cuda", generator=g) * 0.1
+    rows = torch.arange(M, device="cuda") // rps
+    x_ref = (x + rs[rows, None] * delta.float()).requires_grad_(True)
+    h_ref = torch.nn.functional.layer_norm(x_ref, (C,), gamma, beta, 1e-6)
+    x_out, h, mean, rstd = K.ln_fwd(x, gamma, beta, delta=delta, rowscale=rs, rows_per_sample=rps, act_dtype=act)
+    tol = 6e-3 if act == BF16 else 2e-6
+    assert rel(x_out, x_ref.detach()) < 1e-6
+    assert rel(h.float(), h_ref.detach()) < tol
+    dh = torch.randn(M, C, device="cuda", generator=g).to(act)
+    dx_in = torch.randn(M, C, device="cuda", generator=g)
+    h_ref.backward(dh.float())
+    dx, gout = K.ln_bwd(dh, x_out, mean, rstd, gamma, dx_in=dx_in, rowscale=rs, rows_per_sample=rps, want_g=True)
+    ref = dx_in + x_ref.grad
+    assert rel(dx, ref) < (1e-5 if act == BF16 else 2e-6) * 10
+    assert rel(gout.float(), ref * rs[rows, None]) < tol
+    # plain LN without residual
+    _, h2, _, _ = K.ln_fwd(x, gamma, beta, act_dtype=act)
+    assert rel(h2.float(), torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-6)) < tol
+
+
+@pytest.mark.parametrize("M,Kd,R,S", [(1000, 768, 16, 3), (50432, 768, 16, 4), (333, 3072, 8, 1), (700, 1024, 32, 4)])
+def test_adapter_rows_fwd(K, M, Kd, R, S):
+    Rp = K.round_rank(R)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(M, Kd, device="cuda", generator=g).to(BF16)
+    A = torch.zeros(Kd, Rp, device="cuda"); A[:, :R] = torch.randn(Kd, R, device="cuda", generator=g) * 0.2
+    sc = torch.zeros(S, Rp, device="cuda"); sc[:, :R] = torch.randn(S, R, device="cuda", generator=g)
+    a_t = A.to(BF16).t().contiguous()
+    T, U = K.adapter_rows_fwd(x, a_t, sc)
+    Tref = x.float() @ a_t.float().t()
+    assert rel(T, Tref) < 1e-5
+    Uref = torch.cat([Tref * sc[s] for s in range(S)], 1)
+    assert rel(U.float(), Uref) < 6e-3
+    assert float(U[:, R:Rp].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,R,S", [(1000, 2304, 16, 3), (50432, 768, 16, 1), (515, 3072, 8, 4), (700, 4096, 32, 4)])
+def test_adapter_rows_bwd(K, M, N, R, S):
+    Rp = K.round_rank(R)
+    w = N // S
+    g = torch.Generator(device="cuda").manual_seed(4)
+    G = torch.randn(M, N, device="cuda", generator=g).to(BF16)
+    Bf = torch.zeros(w, Rp, device="cuda"); Bf[:, :R] = torch.randn(w, R, device="cuda", generator=g) * 0.2
+    sc = torch.zeros(S, Rp, device="cuda"); sc[:, :R] = torch.randn(S, R, device="cuda", generator=g)
+    T = torch.randn(M, Rp, device="cuda", generator=g)
+    b_t = Bf.to(BF16).t().contiguous()
+    dT, dsc = K.adapter_rows_bwd(G, b_t, sc, T)
+    dU = [G[:, s * w:(s + 1) * w].float() @ b_t.float().t() for s in range(S)]
+    assert rel(dT.float(), sum(dU[s] * sc[s] for s in range(S))) < 6e-3
+    assert rel(dsc, torch.stack([(dU[s] * T).sum(0) for s in range(S)])) < 1e-4
+
+
+@pytest.mark.parametrize("M,Kc,R,S", [(1000, 768, 16, 1), (50432, 2304, 16, 3), (515, 3072, 8, 4), (700, 1024, 32, 1),
+                                      (50432, 3072, 16, 1)])
+def test_adapter_cols(K, M, Kc, R, S):
+    Rp = K.round_rank(R)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(M, Kc, device="cuda", generator=g).to(BF16)
+    V = torch.randn(M, S * Rp, device="cuda", generator=g).to(BF16)
+    out, cs = K.adapter_cols(X, V, S, Rp, want_colsum=True)
+    w = Kc // S
+    ref = sum(X[:, s * w:(s + 1) * w].float().t() @ V[:, s * Rp:(s + 1) * Rp].float() for s in range(S))
+    assert rel(out, ref) < 1e-4
+    assert rel(cs, X.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("B,N,H,D", [(3, 197, 12, 64), (2, 257, 16, 80), (2, 64, 4, 64), (1, 50, 2, 64)])
+def test_attention_fwd_bwd(K, B, N, H, D):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    C = H * D
+    qkv = (torch.randn(B, N, 3, H, D, device="cuda", generator=g) * 1.0).to(BF16)
+    scale = D ** -0.5
+    o, lse = K.attn_fwd(qkv.view(-1), B, N, H, D, scale)
+    q, k, v = [t.float().requires_grad_(True) for t in qkv.permute(2, 0, 3, 1, 4)]
+    att = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+    oref = (att @ v).transpose(1, 2).reshape(B * N, C)
+    assert rel(o.float(), oref.detach()) < 6e-3
+    lref = torch.logsumexp((q @ k.transpose(-2, -1)) * scale, -1) / math.log(2.0)
+    assert rel(lse, lref.detach()) < 1e-4
+    d_o = torch.randn(B * N, C, device="cuda", generator=g).to(BF16)
+    oref.backward(d_o.float())
+    dqkv = K.attn_bwd(qkv.view(-1), o, lse, d_o, B, N, H, D, scale).view(B, N, 3, H, D)
+    dref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4)
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, :, i].float(), dref[:, :, i]) < 1.2e-2, name
+
+
+def test_patch_embed_path(K):
+    B, S, P, C = 3, 224, 16, 768
+    g = torch.Generator(device="cuda").manual_seed(7)
+    img = torch.randn(B, 3, S, S, device="cuda", generator=g)
+    Wc = torch.randn(C, 3, P, P, device="cuda", generator=g) * 0.03
+    bc = torch.randn(C, device="cuda", generator=g) * 0.1
+    cls = torch.randn(C, device="cuda", generator=g); pos = torch.randn(197, C, device="cuda", generator=g)
+    patches = K.patchify(img, P, 768)
+    pe = K.gemm_cp(patches, Wc.reshape(C, -1).to(BF16).contiguous(), bias=bc)
+    x = K.assemble_tokens(pe, cls, pos, B, 197, C)
+    ref = torch.nn.functional.conv2d(img, Wc, bc, stride=P).flatten(2).transpose(1, 2)
+    ref = torch.cat([cls.expand(B, 1, C), ref], 1) + pos
+    assert rel(x.view(B, 197, C), ref) < 6e-3
+    # ViT-H/14 geometry: K = 588 zero padded to 640
+    patches = K.patchify(img, 14, 640)
+    ref = torch.nn.functional.unfold(img, 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert rel(patches[:, :588].float(), ref) < 6e-3 and float(patches[:, 588:].float().abs().max()) == 0.0
+
+
+def test_merge_adamw_sgemm(K):
+    g = torch.Generator(device="cuda").manual_seed(8)
+    N, Kd, R, S = 2304, 768, 16, 3
+    W = torch.randn(N, Kd, device="cuda", generator=g) * 0.02
+    A = torch.randn(Kd, R, device="cuda", generator=g) * 0.2
+    Bf = torch.randn(N // S, R, device="cuda", generator=g) * 0.2
+    cs = torch.randn(S, R, device="cuda", generator=g)
+    ref = W + torch.cat([(Bf * cs[s]) @ A.t() for s in range(S)], 0)
+    assert rel(K.merge_weights(W, A, Bf, cs).float(), ref) < 4e-3
+    p = torch.randn(12345, device="cuda", generator=g); pr = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([pr], lr=1e-3, weight_decay=1e-4)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(12345, device="cuda", generator=g)
+        pr.grad = gr.clone(); opt.step()
+        K.adamw_step(p, gr, m, v, 1e-3, step)
+        assert rel(p, pr.detach()) < 1e-6
+    a = torch.randn(77, 130, device="cuda", generator=g); b = torch.randn(100, 130, device="cuda", generator=g)
+    bias = torch.randn(100, device="cuda", generator=g)
+    assert rel(K.sgemm(a, b.t(), bias=bias), a @ b.t() + bias) < 1e-5
+    assert rel(K.sgemm(a.t(), a), a.t() @ a) < 1e-5
