@@ -1,0 +1,207 @@
+"""Autograd glue over the C-ABI kernels: each class is one differentiable unit of the CaRA hot path.
+
+Forward/backward math follows SURVEY Appendix A.1/A.2 (verified there against the reference's autograd):
+for every adapted projection  Y = X W^T + b_eff + sum_slices [(X A) (.) cs_s] B^T  and, with G = dY,
+  dX = G W + dThat A^T,  dThat = sum_s cs_s (.) (G_s B),  dA = X^T dThat,  dB = sum_s G_s^T Uhat_s,
+  dcs_s = sum_m (G_s B) (.) (X A),  db_eff = sum_m G.
+Frozen weights receive no gradient (vit_cp.py:176-182) and no [K,N]-sized dW is ever formed.
+"""
+import torch
+
+from . import _lib as L
+from . import kernels as K
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class FrozenLinear:
+    """bf16 working copies of one frozen nn.Linear: W [N,K] for the forward GEMM, W^T [K,N] for dX."""
+
+    __slots__ = ("w", "wt", "bias", "key")
+
+    def __init__(self, lin):
+        self.refresh(lin)
+
+    def refresh(self, lin):
+        w = lin.weight.detach()
+        self.w = w.to(BF16).contiguous()
+        self.wt = w.t().to(BF16).contiguous()
+        self.bias = None if lin.bias is None else lin.bias.detach().to(F32).contiguous()
+        self.key = (lin.weight.data_ptr(), lin.weight._version, lin.weight.device,
+                    None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
+
+    @staticmethod
+    def of(lin):
+        fz = lin.__dict__.get("_cara_frozen")
+        key = (lin.weight.data_ptr(), lin.weight._version, lin.weight.device,
+               None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
+        if fz is None or fz.key != key:
+            fz = FrozenLinear(lin)
+            lin.__dict__["_cara_frozen"] = fz
+        return fz
+
+
+class AdapterOperands:
+    """bf16 / padded forms of one projection's staged factors (not differentiable; built once per step)."""
+
+    __slots__ = ("a_t", "a_pad", "b_t", "b_pad", "cs_pad", "rank", "rp", "slices")
+
+    def __init__(self, a_pad, a_t, b_pad, b_t, cs_pad, rank):
+        self.a_pad, self.a_t, self.b_pad, self.b_t, self.cs_pad = a_pad, a_t, b_pad, b_t, cs_pad
+        self.rank, self.rp, self.slices = rank, cs_pad.shape[1], cs_pad.shape[0]
+
+    @staticmethod
+    def build(A, Bf, cs):
+        R = A.shape[1]
+        Rp = K.round_rank(R)
+        a_pad, a_t = pad_cast(A, Rp)
+        b_pad, b_t = pad_cast(Bf, Rp)
+        cs_pad = torch.nn.functional.pad(cs.detach().to(F32), (0, Rp - R)).contiguous()
+        return AdapterOperands(a_pad, a_t, b_pad, b_t, cs_pad, R)
+
+
+def pad_cast(F, Rp):
+    """fp32 [rows,R] -> (bf16 [rows,Rp] zero padded, bf16 [Rp,rows])."""
+    Fp = torch.nn.functional.pad(F.detach(), (0, Rp - F.shape[1])).to(BF16).contiguous()
+    return Fp, Fp.t().contiguous()
+
+
+def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True):
+    T = U = None
+    if ops is not None:
+        T, U = K.adapter_rows_fwd(x, ops.a_t, ops.cs_pad)
+        y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_pad, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
+    else:
+        y = K.gemm_cp(x, fz.w, bias=bias_eff, epi=epi, want_pre=want_pre)
+    return y, T, U
+
+
+def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None):
+    """Returns (dx, dA, dcs, dB, dbias)."""
+    epi = L.EPI_DGELU if dgelu_aux is not None else L.EPI_NONE
+    if ops is None:
+        dx = K.gemm_cp(G, fz.wt, epi=epi, aux=dgelu_aux) if need_dx else None
+        return dx, None, None, None, None
+    R = ops.rank
+    dT, dcs = K.adapter_rows_bwd(G, ops.b_t, ops.cs_pad, T)
+    dx = None
+    if need_dx:
+        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_pad, ext_slices=1, epi=epi, aux=dgelu_aux)
+    dA, _ = K.adapter_cols(x, dT, 1, ops.rp)
+    dB, colsum = K.adapter_cols(G, U, ops.slices, ops.rp, want_colsum=need_bias)
+    return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum
+
+
+class CPLinearFunction(torch.autograd.Function):
+    """One CP-adapted frozen projection (qkv: cara.py:25-42, proj: cara.py:50-58)."""
+
+    @staticmethod
+    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops):
+        y, T, U = _cp_linear_fwd(x, fz, bias_eff if bias_eff is not None else fz.bias, ops)
+        ctx.fz, ctx.ops = fz, ops
+        ctx.save_for_backward(x, T, U)
+        return y
+
+    @staticmethod
+    def backward(ctx, G):
+        x, T, U = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        dx, dA, dcs, dB, dbias = _cp_linear_bwd(G.contiguous(), x, ctx.fz, ctx.ops, T, U, ni[0], ni[4])
+        return dx, dA, dcs, dB, dbias, None, None
+
+
+class CPMlpFunction(torch.autograd.Function):
+    """cp_mlp (cara.py:72-95): fc1 + adapter -> exact-erf GELU -> fc2 + adapter, as one unit so the
+    GELU is applied in the fc1 GEMM epilogue and its derivative in the fc2 dX GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, fz1, ops1, fz2, ops2):
+        train = any(ctx.needs_input_grad)
+        (u, g), T1, U1 = _cp_linear_fwd(x, fz1, bias1 if bias1 is not None else fz1.bias, ops1, epi=L.EPI_GELU,
+                                        want_pre=train)
+        y, T2, U2 = _cp_linear_fwd(g, fz2, bias2 if bias2 is not None else fz2.bias, ops2)
+        ctx.fz1, ctx.ops1, ctx.fz2, ctx.ops2 = fz1, ops1, fz2, ops2
+        ctx.save_for_backward(x, u, g, T1, U1, T2, U2)
+        return y
+
+    @staticmethod
+    def backward(ctx, G):
+        x, u, g, T1, U1, T2, U2 = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        du, dA2, dcs2, dB2, db2 = _cp_linear_bwd(G.contiguous(), g, ctx.fz2, ctx.ops2, T2, U2, True, ni[8],
+                                                 dgelu_aux=u)
+        dx, dA1, dcs1, dB1, db1 = _cp_linear_bwd(du, x, ctx.fz1, ctx.ops1, T1, U1, ni[0], ni[4])
+        return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None
+
+
+class AttnCoreFunction(torch.autograd.Function):
+    """softmax(q k^T D^-1/2) v on the fused projection's [B,N,3,H,D] output (cara.py:44-48)."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, N, H, D, scale):
+        o, lse = K.attn_fwd(qkv, B, N, H, D, scale, want_lse=True)
+        ctx.dims = (B, N, H, D, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        B, N, H, D, scale = ctx.dims
+        return K.attn_bwd(qkv, o, lse, d_o.contiguous(), B, N, H, D, scale), None, None, None, None, None
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """h = LN(x) for the first block / final norm (frozen affine).  x fp32 [M,C]."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, act_dtype):
+        _, h, mean, rstd = K.ln_fwd(x, gamma, beta, eps=eps, act_dtype=act_dtype)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        dx, _ = K.ln_bwd(dh.contiguous(), x, mean, rstd, gamma)
+        return dx, None, None, None, None
+
+
+class AddLayerNormFunction(torch.autograd.Function):
+    """x_new = x + rowscale * delta (residual + DropPath), h = LN(x_new): timm Block's
+    ``x + drop_path(f(norm(x)))`` re-associated so the add rides in the next LayerNorm's pass."""
+
+    @staticmethod
+    def forward(ctx, x, delta, rowscale, gamma, beta, eps, rows_per_sample):
+        x_new, h, mean, rstd = K.ln_fwd(x, gamma, beta, delta=delta, rowscale=rowscale,
+                                        rows_per_sample=rows_per_sample, eps=eps, act_dtype=delta.dtype)
+        ctx.rps = rows_per_sample
+        ctx.save_for_backward(x_new, mean, rstd, gamma, rowscale)
+        return x_new, h
+
+    @staticmethod
+    def backward(ctx, dx_new, dh):
+        x_new, mean, rstd, gamma, rowscale = ctx.saved_tensors
+        if dh is None:
+            dh = torch.zeros(x_new.shape, device=x_new.device, dtype=BF16)
+        dx, g = K.ln_bwd(dh.contiguous(), x_new, mean, rstd, gamma,
+                         dx_in=None if dx_new is None else dx_new.contiguous(), rowscale=rowscale,
+                         rows_per_sample=ctx.rps, want_g=True)
+        return dx, g, None, None, None, None, None
+
+
+class HeadFunction(torch.autograd.Function):
+    """logits = h W^T + b for the trainable classifier (vit_cp.py:166), fp32 SIMT GEMMs."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias):
+        ctx.save_for_backward(h, weight)
+        return K.sgemm(h, weight.t(), bias=bias)
+
+    @staticmethod
+    def backward(ctx, dl):
+        h, weight = ctx.saved_tensors
+        dl = dl.contiguous()
+        dh = K.sgemm(dl, weight) if ctx.needs_input_grad[0] else None
+        dw = K.sgemm(dl.t(), h)
+        return dh, dw, dl.sum(0)

@@ -126,7 +126,8 @@ def test_adapter_rows_fwd(K, M, Kd, R, S):
     assert rel(T, Tref) < 1e-5
     Uref = torch.cat([Tref * sc[s] for s in range(S)], 1)
     assert rel(U.float(), Uref) < 6e-3
-    assert float(U[:, R:Rp].float().abs().max()) == 0.0
+    if R < Rp:
+        assert float(U[:, R:Rp].float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("M,N,R,S", [(1000, 2304, 16, 3), (50432, 768, 16, 1), (515, 3072, 8, 4), (700, 4096, 32, 4)])

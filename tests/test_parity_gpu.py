@@ -1,0 +1,151 @@
+"""Model-level parity (GPU): the CUDA path behind the reference's API vs. the CPU oracle and the golden
+vectors produced by the reference itself.  Bars (BASELINE.json north_star): bf16 mode logits rel-err <= 1e-2,
+CP-factor-grad cosine >= 0.999."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cara_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().cpu(); b = torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a = torch.as_tensor(a).double().cpu().flatten(); b = torch.as_tensor(b).double().cpu().flatten()
+    return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def build(g, scale, drop_path=0.0, model_name="vit_base_patch16_224_in21k", **kw):
+    from cara_b200.vit import create_model
+    from src.cara.cara import cara
+    vit = create_model(model_name, drop_path_rate=drop_path, depth=g.depth, embed_dim=g.embed_dim,
+                       num_heads=g.num_heads, patch_size=g.patch, img_size=g.img, **kw)
+    vit = cara({"model": vit, "rank": g.rank, "scale": scale, "l_mu": 1.0, "l_std": 0.0})
+    vit.reset_classifier(g.num_classes)
+    st = O.synthetic_state(g)
+    vit.load_state_dict(st, strict=True)
+    for n, p in vit.named_parameters():          # vit_cp.py:176-182
+        p.requires_grad = ("CP" in n or "head" in n)
+    return vit.cuda(), st
+
+
+def run_step(vit, x, y):
+    vit.zero_grad(set_to_none=True)
+    logits = vit(x.cuda())
+    loss = torch.nn.functional.cross_entropy(logits, y.cuda())
+    loss.backward()
+    grads = {n: p.grad.detach().cpu() for n, p in vit.named_parameters() if p.grad is not None}
+    return logits.detach().cpu(), float(loss), grads
+
+
+def check_against(logits, loss, grads, ref_logits, ref_loss, ref_grads, tag):
+    e = rel(logits, ref_logits)
+    assert e <= 1e-2, "%s: logits rel-err %.3e > 1e-2" % (tag, e)
+    assert abs(loss - ref_loss) <= 2e-2 * max(1.0, abs(ref_loss)), (tag, loss, ref_loss)
+    worst = min((cos(grads[k], ref_grads[k]), k) for k in ref_grads)
+    assert worst[0] >= 0.999, "%s: grad cosine %s" % (tag, worst)
+    for k in ref_grads:
+        assert rel(grads[k], ref_grads[k]) < 6e-2, (tag, k, rel(grads[k], ref_grads[k]))
+    return e, worst
+
+
+def test_vitb_r16_matches_reference_golden_and_oracle():
+    """Full ViT-B/16, rank 16, 100 classes, B=2: against the reference's own outputs (golden) and the oracle."""
+    z = np.load(os.path.join(G, "ref_vitb_d12_r16_fp32.npz"))
+    g = O.Geometry(depth=12, rank=16, num_classes=100)
+    vit, st = build(g, float(z["scale"]))
+    vit.eval()
+    x, y = O.synthetic_batch(g, int(z["batch"]))
+    logits, loss, grads = run_step(vit, x, y)
+    ref_grads = {k[5:]: z[k] for k in z.files if k.startswith("grad.")}
+    e, worst = check_against(logits, loss, grads, z["logits"], float(z["loss"]), ref_grads, "golden")
+    print("ViT-B r16 vs reference golden: logits rel %.3e, worst grad cosine %.6f (%s)" % (e, worst[0], worst[1]))
+    o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, float(z["scale"]))
+    check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, "oracle")
+
+
+@pytest.mark.parametrize("geom,batch,scale", [
+    (dict(depth=2, rank=8, num_classes=10), 3, 2.5),
+    (dict(depth=3, rank=32, num_classes=37), 2, 0.5),
+    (dict(embed_dim=1024, depth=2, num_heads=16, rank=32, num_classes=100), 2, 1.0),          # ViT-L width
+    (dict(embed_dim=1280, depth=2, num_heads=16, patch=14, rank=32, num_classes=100), 2, 1.0),  # ViT-H/14, 257 tokens
+])
+def test_reduced_depth_geometries_vs_oracle(geom, batch, scale):
+    g = O.Geometry(**geom)
+    vit, st = build(g, scale)
+    vit.eval()
+    x, y = O.synthetic_batch(g, batch)
+    logits, loss, grads = run_step(vit, x, y)
+    o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, scale)
+    check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, str(geom))
+
+
+def test_halves_match_reference_golden():
+    """Bound cp_attn / cp_mlp forwards of block 1 against the reference's own outputs."""
+    z = np.load(os.path.join(G, "ref_halves_fp64.npz"))
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    vit, _ = build(g, float(z["scale"]))
+    vit.eval()
+    blk = vit.blocks[int(z["layer"])]
+    assert (blk.attn.attn_idx, blk.attn.idx, blk.mlp.idx) == (int(z["attn_idx"]), int(z["idx"]), int(z["mlp_idx"]))
+    x = torch.from_numpy(z["x"]).float().cuda()
+    with torch.no_grad():
+        a = blk.attn(x); m = blk.mlp(x)
+    assert a.dtype == torch.float32 and a.shape == x.shape
+    assert rel(a, z["attn"]) < 1e-2 and rel(m, z["mlp"]) < 1e-2
+
+
+def test_train_mode_droppath_replay():
+    """Stochastic depth: replay the per-sample multipliers the CUDA path drew through the oracle."""
+    g = O.Geometry(depth=3, rank=16, num_classes=10)
+    vit, st = build(g, 1.0, drop_path=0.5)
+    vit.train()
+    import warnings
+    drawn = []
+    from cara_b200 import vit as V
+    orig = V.DropPath.rowscale
+
+    def spy(self, batch, device):
+        rs = orig(self, batch, device)
+        drawn.append(None if rs is None else rs.detach().cpu())
+        return rs
+    V.DropPath.rowscale = spy
+    try:
+        x, y = O.synthetic_batch(g, 4)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            logits, loss, grads = run_step(vit, x, y)
+    finally:
+        V.DropPath.rowscale = orig
+    keep = torch.ones(g.depth, 2, 4)
+    it = iter(drawn)
+    for l in range(g.depth):
+        for j in range(2):
+            if isinstance(vit.blocks[l].drop_path, V.DropPath):
+                rs = next(it)
+                if rs is not None:
+                    keep[l, j] = rs
+    o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, 1.0, keep=keep)
+    check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, "droppath")
+
+
+def test_reference_forward_shape():
+    """tests/test_cara.py:93-98 of the reference (train mode, default init), on the GPU."""
+    from cara_b200.vit import create_model
+    from src.cara.cara import cara
+    torch.manual_seed(0)
+    vit = cara({"model": create_model("vit_base_patch16_224_in21k", drop_path_rate=0.1), "rank": 32, "scale": 1.0,
+                "l_mu": 1.0, "l_std": 0.0}).cuda()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = vit(torch.randn((2, 3, 224, 224)).cuda())
+    assert tuple(out.shape) == (2, 21843)
