@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the CaRA fine-tuning hot path on B200 (BASELINE.json: fine-tune images/sec, ViT-B/16 CaRA r16).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's CPU path, oracle port, host cores)
+
+One "step" = one fine-tune iteration (reference vit_cp.py:45-50: forward, CE, backward, AdamW over CP*+head) on
+a synthetic batch of 256 images per GPU (weak scaling; frozen backbone replicated, one NCCL all-reduce of the flat
+CP+head gradient per step).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1] (the metric's configuration) and the larger data-parallel ones
+    "vitb16_r16": dict(model="vit_base_patch16_224_in21k", embed_dim=768, depth=12, num_heads=12, patch=16, rank=16,
+                       batch=256, gflop_per_image=74.24),
+    "vitl16_r32": dict(model="vit_large_patch16_224_in21k", embed_dim=1024, depth=24, num_heads=16, patch=16, rank=32,
+                       batch=256, gflop_per_image=264.60),
+    "vith14_r32": dict(model="vit_huge_patch14_224_in21k", embed_dim=1280, depth=32, num_heads=16, patch=14, rank=32,
+                       batch=128, gflop_per_image=711.95),
+}
+NUM_CLASSES = 100
+METRIC = "fine-tune images/sec, ViT-B/16 CaRA r16, 1/2/4/8 B200; fused GEMM % TC peak"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle-reason samples taken DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(cfg, device):
+    import torch
+    from cara_b200 import train as T
+    from cara_b200.vit import create_model
+    from oracle_free_init import init_synthetic  # noqa: F401  (defined below, injected into sys.modules)
+    from src.cara.cara import cara
+    torch.manual_seed(0)
+    vit = create_model(cfg["model"], drop_path_rate=0.1)
+    vit = cara({"model": vit, "rank": cfg["rank"], "scale": 1.0, "l_mu": 1.0, "l_std": 0.1})
+    vit.reset_classifier(NUM_CLASSES)
+    init_synthetic(vit, cfg["rank"])
+    vit = vit.to(device)
+    trainable = T.freeze_backbone(vit)
+    opt = T.FusedAdamW(T.FlatTrainable(trainable), lr=1e-3, weight_decay=1e-4)
+    vit.train()
+    return vit, opt
+
+
+def _install_init_module():
+    """Random-init weights of the architecture + non-default CP factors (the reference's default init makes every
+    delta exactly zero, cara.py:128,132; SURVEY D.3 recipe keeps the adapter numerically alive)."""
+    import types
+
+    import torch
+
+    def init_synthetic(vit, rank):
+        g = torch.Generator().manual_seed(1234)
+        sa, sp = (0.01 / rank ** 0.5) ** 0.25, (0.01 / rank ** 0.5) ** (1.0 / 3.0)
+        with torch.no_grad():
+            for n, p in vit.named_parameters():
+                if n.startswith("CP_A"):
+                    p.copy_(torch.randn(p.shape, generator=g) * sa)
+                elif n.startswith("CP_P"):
+                    p.copy_(torch.randn(p.shape, generator=g) * sp)
+                elif n.startswith("CP_bias"):
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+                elif n.endswith(".bias"):
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    mod = types.ModuleType("oracle_free_init")
+    mod.init_synthetic = init_synthetic
+    sys.modules["oracle_free_init"] = mod
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from cara_b200 import kernels as K
+    from cara_b200 import train as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _install_init_module()
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg["batch"]
+    vit, opt = build_model(cfg, dev)
+    img = 224
+    g = torch.Generator().manual_seed(4321 + rank)
+    host_x = [torch.randn(B, 3, img, img, generator=g).pin_memory() for _ in range(2)]
+    host_y = [torch.randint(0, NUM_CLASSES, (B,), generator=g).pin_memory() for _ in range(2)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------ device-resident throughput ("value")
+    for i in range(args.warmup):
+        T.train_step(vit, opt, dev_x[i % 2], dev_y[i % 2], world)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.gemm_events = []
+    launches0 = K.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = T.train_step(vit, opt, dev_x[i % 2], dev_y[i % 2], world)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = K.launch_count - launches0
+    gemm_events, K.gemm_events = K.gemm_events, None
+    clocks = sampler.stop() if rank == 0 else None
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    loss_value = float(loss)
+
+    # ------------------------------------------------------------ end-to-end: host buffers, H2D + D2H in the timed region
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_x = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    stage_y = [torch.empty_like(dev_y[0]) for _ in range(2)]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[s])            # the step that last used this slot has finished
+            stage_x[s].copy_(host_x[s], non_blocking=True)
+            stage_y[s].copy_(host_y[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        losses = []
+        prefetch(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s])
+            l = T.train_step(vit, opt, stage_x[s], stage_y[s], world)
+            done[s].record()
+            loss_host[s].copy_(l.detach(), non_blocking=True)     # D2H read of this step's loss
+            ev = torch.cuda.Event(); ev.record()
+            losses.append((ev, s))
+            if i > 0:                                            # consume the previous step's loss on the host
+                pe, ps = losses[i - 1]
+                pe.synchronize()
+                _ = float(loss_host[ps])
+        losses[-1][0].synchronize()
+        return float(loss_host[losses[-1][1]])
+
+    e2e_loop(2)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(args.steps)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, gemm_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, gemm_ms = [float(v) for v in t]
+    total_images = B * world * args.steps
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": total_images / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 CaRA rank=16 bf16 fine-tune step (fwd + CE + dX-only bwd + factor grads + "
+                               "AdamW over CP*+head), batch 256 per GPU, 224x224, 100 classes, random-init weights"
+                   if args.config == "vitb16_r16" else args.config,
+                   "config_key": args.config, "batch_per_gpu": B, "global_batch": B * world, "tokens": 197,
+                   "parallelism": "dp%d" % world, "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2",
+                   "drop_path": 0.1, "weight_dropout": "not applied (documented deviation)",
+                   "algorithmic_gflop_per_image": cfg["gflop_per_image"]},
+        "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 8), "d2h_bytes_per_step": 4,
+                "note": "pinned host batches, copy stream prefetch, loss read back every step"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_cp_kernel (fused CP projections fwd + dX, %d launches)" % len(gemm_events),
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": None, "peak_source": peak_src,
+                     "step_frac_of_peak": cfg["gflop_per_image"] * 1e9 * B / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
+        "loss": loss_value,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference(args, steps, warmup):
+    """The reference's CPU path (oracle port of cara.py + timm/tensorly semantics, train mode as shipped:
+    weight dropout 0.1, DropPath 0.1, autograd through the materialised deltas, AdamW) on the host cores."""
+    import torch
+    from oracle import cara_oracle as O
+    cfg = CONFIGS[args.config]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = O.Geometry(embed_dim=cfg["embed_dim"], depth=cfg["depth"], num_heads=cfg["num_heads"], patch=cfg["patch"],
+                   num_classes=NUM_CLASSES, rank=cfg["rank"])
+    st = O.synthetic_state(g)
+    bs = args.cpu_batch
+    x, y = O.synthetic_batch(g, bs)
+    opt = {}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(st, opt, i + 1, g, x, y, 1.0, train=True, wdrop=0.1, drop_path=0.1)
+        times.append(time.perf_counter() - t0)
+    best = min(times[warmup:])
+    return {"value": bs / best, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "%d timed steps (best of, after %d warm-up) of the same ViT-B/16 r16 train step at batch %d on "
+                      "the host CPU (oracle/cara_oracle.py: materialised deltas + weight dropout as the reference)"
+                      % (steps, warmup, bs), "sec_per_step": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=max(1, min(args.warmup, 1)))
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": base["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "ViT-B/16 CaRA rank=16 fine-tune step on the host CPU, batch %d sample" % args.cpu_batch,
+                      "config_key": args.config},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cara_b200", choices=["cara_b200", "reference"])
+    ap.add_argument("--config", default="vitb16_r16", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

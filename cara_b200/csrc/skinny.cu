@@ -2,12 +2,18 @@
 // [M, K] activation / gradient matrix exactly once through a cp.async ring and contracts it against a
 // rank-R operand with warp-level mma.sync (the tensor pipe is irrelevant here -- bytes are the cost).
 //
+// Precision: the rank-R path has only R terms per output, so bf16 rounding of its operands does not average
+// out the way it does over K = 768..5120 in the frozen GEMM.  Factors and low-rank activations are therefore
+// carried as bf16 (hi, lo) pairs (x = hi + lo, ~16 mantissa bits): factor matrices arrive as [hi rows; lo rows],
+// the two partial products are folded in fp32, and Uhat / dThat are emitted as [hi | lo | hi] column blocks so
+// that the tcgen05 GEMM's adapter segment computes hi*Bhi + lo*Bhi + hi*Blo against [Bhi | Bhi | Blo].
+//
 //   rows_kernel (row-wise, K reduced):
-//     fwd : T = X A                     [M,Rp] fp32 (saved),  Uhat_s = cs_s (.) T   [M,S*Rp] bf16
-//     bwd : dU_s = G_s B  per slice s,  dThat = sum_s cs_s (.) dU_s  [M,Rp] bf16,
+//     fwd : T = X A                     [M,Rp] fp32 (saved),  Uhat_s = cs_s (.) T   [M,S*3Rp] bf16 (hi|lo|hi)
+//     bwd : dU_s = G_s B  per slice s,  dThat = sum_s cs_s (.) dU_s  [M,3Rp] bf16 (hi|lo|hi),
 //           dcs_s = sum_m dU_s (.) T    [S,Rp] fp32 (atomically accumulated)
 //   cols_kernel (column-wise, M reduced):
-//     out[k,:] += sum_m X[m,k] V[m, slice(k)*Rp : +Rp]   (dA = X^T dThat,  dB = sum_s G_s^T Uhat_s)
+//     out[k,:] += sum_m X[m,k] (Vhi + Vlo)[m, slice(k)]   (dA = X^T dThat,  dB = sum_s G_s^T Uhat_s)
 //     colsum[k] += sum_m X[m,k]                          (adapter-bias gradient)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -50,8 +56,9 @@ template <int RT, int CS>
 __global__ void __launch_bounds__(256)
 rows_kernel(const RowsArgs a) {
   constexpr int RP = RT * 8;
+  constexpr int NT = 2 * RT;                       // n-tiles incl. the lo halves of the factor
   constexpr int XS_BYTES = R_BM * R_BK * 2;        // 16 KB
-  constexpr int FS_BYTES = RP * R_BK * 2;
+  constexpr int FS_BYTES = 2 * RP * R_BK * 2;
   constexpr int ST_BYTES = XS_BYTES + FS_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float red[CS * RP];
@@ -73,19 +80,19 @@ rows_kernel(const RowsArgs a) {
         const __nv_bfloat16* src = a.X + static_cast<size_t>(ok ? m0 + row : 0) * a.ldx + kcol + ch * 8;
         cp_async16(xs + row * 128 + ((ch ^ (row & 7)) << 4), src, ok);
       }
-      if (tid < RP * 8) {
-        const int row = tid >> 3, ch = tid & 7;
+      for (int idx = tid; idx < 2 * RP * 8; idx += 256) {
+        const int row = idx >> 3, ch = idx & 7;
         cp_async16(fs + row * 128 + ((ch ^ (row & 7)) << 4), a.Ft + static_cast<size_t>(row) * a.ldf + fcol + ch * 8, true);
       }
     }
     cp_async_commit();
   };
 
-  float acc[CS][RT][4];
+  float acc[CS][NT][4];
 #pragma unroll
   for (int s = 0; s < CS; ++s)
 #pragma unroll
-    for (int j = 0; j < RT; ++j)
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[s][j][e] = 0.f;
 
@@ -107,7 +114,7 @@ rows_kernel(const RowsArgs a) {
           ldsm_x4(xs + row * 128 + ((ch ^ (row & 7)) << 4), af);
         }
 #pragma unroll
-        for (int jp = 0; jp < RT / 2; ++jp) {
+        for (int jp = 0; jp < NT / 2; ++jp) {
           uint32_t bf[4];
           const int n = jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, ch = kk * 2 + ((lane >> 3) & 1);
           ldsm_x4(fs + n * 128 + ((ch ^ (n & 7)) << 4), bf);
@@ -122,8 +129,24 @@ rows_kernel(const RowsArgs a) {
   const int g = lane >> 2, t = lane & 3;
   const int r_lo = m0 + warp * 16 + g, r_hi = r_lo + 8;
   const bool ok_lo = r_lo < a.M, ok_hi = r_hi < a.M;
+  // fold the (factor hi, factor lo) partial products
+#pragma unroll
+  for (int s = 0; s < CS; ++s)
+#pragma unroll
+    for (int j = 0; j < RT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[s][j][e] += acc[s][j + RT][e];
+  // emit v as the bf16 column blocks [hi | lo | hi] at row pointer p (block pitch RP)
+  auto emit = [&](__nv_bfloat16* p, int col, float v0, float v1) {
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+    const float2 hf = __bfloat1622float2(hi);
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint32_t*>(p + col) = h;
+    *reinterpret_cast<uint32_t*>(p + RP + col) = pack2(v0 - hf.x, v1 - hf.y);
+    *reinterpret_cast<uint32_t*>(p + 2 * RP + col) = h;
+  };
   if (a.mode == 0) {
-    // forward: T (fp32) and the per-slice scaled bf16 operand for the GEMM's adapter segment
+    // forward: T (fp32) and the per-slice scaled operand for the GEMM's adapter segment
 #pragma unroll
     for (int j = 0; j < RT; ++j) {
       const int col = j * 8 + 2 * t;
@@ -131,8 +154,8 @@ rows_kernel(const RowsArgs a) {
       if (ok_hi) *reinterpret_cast<float2*>(a.T + static_cast<size_t>(r_hi) * RP + col) = make_float2(acc[0][j][2], acc[0][j][3]);
       for (int so = 0; so < a.s_out; ++so) {
         const float2 sc = *reinterpret_cast<const float2*>(a.scales + so * RP + col);
-        if (ok_lo) *reinterpret_cast<uint32_t*>(a.U + static_cast<size_t>(r_lo) * a.ldu + so * RP + col) = pack2(sc.x * acc[0][j][0], sc.y * acc[0][j][1]);
-        if (ok_hi) *reinterpret_cast<uint32_t*>(a.U + static_cast<size_t>(r_hi) * a.ldu + so * RP + col) = pack2(sc.x * acc[0][j][2], sc.y * acc[0][j][3]);
+        if (ok_lo) emit(a.U + static_cast<size_t>(r_lo) * a.ldu + so * 3 * RP, col, sc.x * acc[0][j][0], sc.y * acc[0][j][1]);
+        if (ok_hi) emit(a.U + static_cast<size_t>(r_hi) * a.ldu + so * 3 * RP, col, sc.x * acc[0][j][2], sc.y * acc[0][j][3]);
       }
     }
   } else {
@@ -162,8 +185,8 @@ rows_kernel(const RowsArgs a) {
           atomicAdd(&red[s * RP + col + 1], p1);
         }
       }
-      if (ok_lo) *reinterpret_cast<uint32_t*>(a.U + static_cast<size_t>(r_lo) * a.ldu + col) = pack2(d0, d1);
-      if (ok_hi) *reinterpret_cast<uint32_t*>(a.U + static_cast<size_t>(r_hi) * a.ldu + col) = pack2(d2, d3);
+      if (ok_lo) emit(a.U + static_cast<size_t>(r_lo) * a.ldu, col, d0, d1);
+      if (ok_hi) emit(a.U + static_cast<size_t>(r_hi) * a.ldu, col, d2, d3);
     }
     __syncthreads();
     for (int i = tid; i < CS * RP; i += 256) atomicAdd(a.dc + i, red[i]);
@@ -172,7 +195,7 @@ rows_kernel(const RowsArgs a) {
 
 template <int RT, int CS>
 static int rows_launch_t(const RowsArgs& a, cudaStream_t st) {
-  constexpr int smem = R_STAGES * (R_BM * R_BK * 2 + RT * 8 * R_BK * 2);
+  constexpr int smem = R_STAGES * (R_BM * R_BK * 2 + 2 * RT * 8 * R_BK * 2);
   static bool done = false;
   if (!done) {
     if (cudaFuncSetAttribute(rows_kernel<RT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -31;
@@ -198,7 +221,8 @@ template <int RT>
 __global__ void __launch_bounds__(256)
 cols_kernel(const ColsArgs a) {
   constexpr int RP = RT * 8;
-  constexpr int VSTR = RP * 2 + 16;                // padded V row pitch (bytes)
+  constexpr int NT = 2 * RT;                       // V carries (hi | lo) column blocks
+  constexpr int VSTR = 2 * RP * 2 + 16;            // padded V row pitch (bytes)
   constexpr int XS_BYTES = C_BM * C_BK * 2;        // 16 KB
   constexpr int VS_BYTES = C_BM * VSTR;
   constexpr int ST_BYTES = XS_BYTES + ((VS_BYTES + 127) / 128) * 128;
@@ -223,21 +247,21 @@ cols_kernel(const ColsArgs a) {
         const __nv_bfloat16* src = a.X + static_cast<size_t>(ok ? mrow0 + row : 0) * a.ldx + k0 + ch * 8;
         cp_async16(xs + row * 512 + ((ch ^ (row & 7)) << 4), src, ok);
       }
-      if (tid < C_BM * RT) {
-        const int row = tid / RT, ch = tid % RT;
+      if (tid < C_BM * NT) {
+        const int row = tid / NT, ch = tid % NT;
         const bool ok = (mrow0 + row) < m_end;
-        const __nv_bfloat16* src = a.V + static_cast<size_t>(ok ? mrow0 + row : 0) * a.ldv + slice * RP + ch * 8;
+        const __nv_bfloat16* src = a.V + static_cast<size_t>(ok ? mrow0 + row : 0) * a.ldv + slice * 3 * RP + ch * 8;
         cp_async16(vs + row * VSTR + ch * 16, src, ok);
       }
     }
     cp_async_commit();
   };
 
-  float acc[2][RT + 1][4];
+  float acc[2][NT + 1][4];
 #pragma unroll
   for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
-    for (int j = 0; j <= RT; ++j)
+    for (int j = 0; j <= NT; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[kt][j][e] = 0.f;
   const uint32_t ones = (lane >> 2) == 0 ? 0x3F803F80u : 0u;   // B fragment of a column of ones (n = 0)
@@ -250,10 +274,10 @@ cols_kernel(const ColsArgs a) {
     const uint32_t xs = sbase + (i % C_STAGES) * ST_BYTES, vs = xs + XS_BYTES;
 #pragma unroll
     for (int ms = 0; ms < C_BM; ms += 16) {
-      uint32_t bf[RT / 2][4];
+      uint32_t bf[NT / 2][4];
       const int q = lane >> 3;
 #pragma unroll
-      for (int jp = 0; jp < RT / 2; ++jp) {
+      for (int jp = 0; jp < NT / 2; ++jp) {
         const int row = ms + (lane & 7) + (q & 1) * 8, ch = jp * 2 + (q >> 1);
         ldsm_x4_t(vs + row * VSTR + ch * 16, bf[jp]);
       }
@@ -263,11 +287,11 @@ cols_kernel(const ColsArgs a) {
         const int row = ms + (lane & 7) + (q >> 1) * 8, ch = (warp * 32 + kt * 16) / 8 + (q & 1);
         ldsm_x4_t(xs + row * 512 + ((ch ^ (row & 7)) << 4), af);
 #pragma unroll
-        for (int jp = 0; jp < RT / 2; ++jp) {
+        for (int jp = 0; jp < NT / 2; ++jp) {
           mma_bf16(acc[kt][jp * 2 + 0], af, bf[jp][0], bf[jp][1]);
           mma_bf16(acc[kt][jp * 2 + 1], af, bf[jp][2], bf[jp][3]);
         }
-        if (a.colsum != nullptr) mma_bf16(acc[kt][RT], af, ones, ones);
+        if (a.colsum != nullptr) mma_bf16(acc[kt][NT], af, ones, ones);
       }
     }
   }
@@ -282,14 +306,14 @@ cols_kernel(const ColsArgs a) {
 #pragma unroll
       for (int j = 0; j < RT; ++j) {
         const int col = j * 8 + 2 * t;
-        atomicAdd(a.out + static_cast<size_t>(orow) * RP + col, acc[kt][j][0]);
-        atomicAdd(a.out + static_cast<size_t>(orow) * RP + col + 1, acc[kt][j][1]);
-        atomicAdd(a.out + static_cast<size_t>(orow + 8) * RP + col, acc[kt][j][2]);
-        atomicAdd(a.out + static_cast<size_t>(orow + 8) * RP + col + 1, acc[kt][j][3]);
+        atomicAdd(a.out + static_cast<size_t>(orow) * RP + col, acc[kt][j][0] + acc[kt][j + RT][0]);
+        atomicAdd(a.out + static_cast<size_t>(orow) * RP + col + 1, acc[kt][j][1] + acc[kt][j + RT][1]);
+        atomicAdd(a.out + static_cast<size_t>(orow + 8) * RP + col, acc[kt][j][2] + acc[kt][j + RT][2]);
+        atomicAdd(a.out + static_cast<size_t>(orow + 8) * RP + col + 1, acc[kt][j][3] + acc[kt][j + RT][3]);
       }
       if (a.colsum != nullptr && t == 0) {
-        atomicAdd(a.colsum + kc, acc[kt][RT][0]);
-        atomicAdd(a.colsum + kc + 8, acc[kt][RT][2]);
+        atomicAdd(a.colsum + kc, acc[kt][NT][0]);
+        atomicAdd(a.colsum + kc + 8, acc[kt][NT][2]);
       }
     }
   }
@@ -297,7 +321,7 @@ cols_kernel(const ColsArgs a) {
 
 template <int RT>
 static int cols_launch_t(ColsArgs a, int num_sms, cudaStream_t st) {
-  constexpr int VSTR = RT * 16 + 16;
+  constexpr int VSTR = 2 * RT * 16 + 16;
   constexpr int smem = C_STAGES * (C_BM * C_BK * 2 + ((C_BM * VSTR + 127) / 128) * 128);
   static bool done = false;
   if (!done) {

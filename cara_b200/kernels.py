@@ -12,6 +12,7 @@ from . import _lib as L
 
 BF16, F32 = torch.bfloat16, torch.float32
 launch_count = 0  # number of cara_* kernel launches issued (bench.py reports it as gpu_launches)
+gemm_events = None  # bench.py: list of (start event, end event, algorithmic flops) per fused-projection launch
 _dev = [None]
 
 
@@ -67,7 +68,14 @@ def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, o
         assert aux is not None and aux.dtype == BF16 and aux.shape == (M, N)
         d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
     d.epi, d.num_sms = epi, num_sms
-    L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
+    if gemm_events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
+        e1.record()
+        gemm_events.append((e0, e1, 2.0 * M * N * (K0 + (d.K1 // 3 if a1 is not None else 0))))
+    else:
+        L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
     return (out, out2) if epi == L.EPI_GELU else out
 
 
@@ -101,38 +109,53 @@ def ln_bwd(dh, x, mean, rstd, gamma, dx_in=None, rowscale=None, rows_per_sample=
     return dx_out, g_out
 
 
-def adapter_rows_fwd(x, a_t, scales):
-    """x bf16 [M,K]; a_t bf16 [Rp,K]; scales fp32 [S,Rp] -> (T fp32 [M,Rp], Uhat bf16 [M,S*Rp])."""
+def split_bf16(F):
+    """fp32 -> (hi, lo) bf16 with hi + lo ~= F to ~16 mantissa bits."""
+    hi = F.to(BF16)
+    return hi, (F - hi.float()).to(BF16)
+
+
+def factor_operands(F, Rp):
+    """fp32 factor [..., rows, R] -> (ext bf16 [..., rows, 3Rp] = [hi|hi|lo], t2 bf16 [..., 2Rp, rows] = [hi^T; lo^T])."""
+    Fp = torch.nn.functional.pad(F.detach().float(), (0, Rp - F.shape[-1]))
+    hi, lo = split_bf16(Fp)
+    ext = torch.cat([hi, hi, lo], dim=-1).contiguous()
+    t2 = torch.cat([hi.transpose(-1, -2), lo.transpose(-1, -2)], dim=-2).contiguous()
+    return ext, t2
+
+
+def adapter_rows_fwd(x, a_t2, scales):
+    """x bf16 [M,K]; a_t2 bf16 [2Rp,K]; scales fp32 [S,Rp] -> (T fp32 [M,Rp], Uhat bf16 [M,S*3Rp])."""
     st = _prep(x)
     M, K = x.shape
-    Rp = a_t.shape[0]
-    S = scales.shape[0]
-    assert a_t.shape == (Rp, K) and a_t.is_contiguous() and scales.shape == (S, Rp) and scales.is_contiguous()
+    S, Rp = scales.shape
+    assert a_t2.shape == (2 * Rp, K) and a_t2.is_contiguous() and scales.is_contiguous() and x.stride(1) == 1
     T = torch.empty((M, Rp), device=x.device, dtype=F32)
-    U = torch.empty((M, S * Rp), device=x.device, dtype=BF16)
-    L.check(L.lib().cara_adapter_rows_fwd(x.data_ptr(), x.stride(0), M, K, a_t.data_ptr(), scales.data_ptr(), S, Rp,
+    U = torch.empty((M, S * 3 * Rp), device=x.device, dtype=BF16)
+    L.check(L.lib().cara_adapter_rows_fwd(x.data_ptr(), x.stride(0), M, K, a_t2.data_ptr(), scales.data_ptr(), S, Rp,
                                           T.data_ptr(), U.data_ptr(), st), "cara_adapter_rows_fwd")
     return T, U
 
 
-def adapter_rows_bwd(g, b_t, scales, T):
-    """g bf16 [M,N]; b_t bf16 [Rp,N/S]; scales [S,Rp]; T fp32 [M,Rp] -> (dThat bf16 [M,Rp], dscales fp32 [S,Rp])."""
+def adapter_rows_bwd(g, b_t2, scales, T):
+    """g bf16 [M,N]; b_t2 bf16 [2Rp,N/S]; scales [S,Rp]; T fp32 [M,Rp] -> (dThat bf16 [M,3Rp], dscales fp32 [S,Rp])."""
     st = _prep(g)
     M, N = g.shape
     S, Rp = scales.shape
-    assert b_t.shape == (Rp, N // S) and b_t.is_contiguous() and T.shape == (M, Rp)
-    dT = torch.empty((M, Rp), device=g.device, dtype=BF16)
+    assert b_t2.shape == (2 * Rp, N // S) and b_t2.is_contiguous() and T.shape == (M, Rp) and g.stride(1) == 1
+    dT = torch.empty((M, 3 * Rp), device=g.device, dtype=BF16)
     dsc = torch.zeros((S, Rp), device=g.device, dtype=F32)
-    L.check(L.lib().cara_adapter_rows_bwd(g.data_ptr(), g.stride(0), M, N, S, b_t.data_ptr(), scales.data_ptr(), Rp,
+    L.check(L.lib().cara_adapter_rows_bwd(g.data_ptr(), g.stride(0), M, N, S, b_t2.data_ptr(), scales.data_ptr(), Rp,
                                           T.data_ptr(), dT.data_ptr(), dsc.data_ptr(), st), "cara_adapter_rows_bwd")
     return dT, dsc
 
 
 def adapter_cols(x, v, slices, Rp, want_colsum=False):
-    """out [Kc/slices, Rp] = sum_s x[:, slice s]^T v[:, s*Rp:+Rp]; colsum [Kc] = column sums of x."""
+    """out [Kc/slices, Rp] = sum_s x[:, slice s]^T (vhi + vlo)[:, slice s]; v bf16 [M, slices*3Rp];
+    colsum [Kc] = column sums of x."""
     st = _prep(x)
     M, Kc = x.shape
-    assert v.shape == (M, slices * Rp) and x.stride(1) == 1 and v.stride(1) == 1
+    assert v.shape == (M, slices * 3 * Rp) and x.stride(1) == 1 and v.stride(1) == 1
     out = torch.zeros((Kc // slices, Rp), device=x.device, dtype=F32)
     cs = torch.zeros(Kc, device=x.device, dtype=F32) if want_colsum else None
     L.check(L.lib().cara_adapter_cols(x.data_ptr(), x.stride(0), M, Kc, v.data_ptr(), v.stride(0), slices, Rp,

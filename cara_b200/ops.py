@@ -42,35 +42,31 @@ class FrozenLinear:
 
 
 class AdapterOperands:
-    """bf16 / padded forms of one projection's staged factors (not differentiable; built once per step)."""
+    """bf16 (hi, lo) forms of one projection's staged factors (not differentiable; built once per step).
+    ``a_ext``/``b_ext``: [rows, 3Rp] = [hi|hi|lo] (adapter segment of the GEMM); ``a_t2``/``b_t2``: [2Rp, rows]
+    (skinny kernels); ``cs_pad``: fp32 [slices, Rp]."""
 
-    __slots__ = ("a_t", "a_pad", "b_t", "b_pad", "cs_pad", "rank", "rp", "slices")
+    __slots__ = ("a_t2", "a_ext", "b_t2", "b_ext", "cs_pad", "rank", "rp", "slices")
 
-    def __init__(self, a_pad, a_t, b_pad, b_t, cs_pad, rank):
-        self.a_pad, self.a_t, self.b_pad, self.b_t, self.cs_pad = a_pad, a_t, b_pad, b_t, cs_pad
+    def __init__(self, a_ext, a_t2, b_ext, b_t2, cs_pad, rank):
+        self.a_ext, self.a_t2, self.b_ext, self.b_t2, self.cs_pad = a_ext, a_t2, b_ext, b_t2, cs_pad
         self.rank, self.rp, self.slices = rank, cs_pad.shape[1], cs_pad.shape[0]
 
     @staticmethod
     def build(A, Bf, cs):
         R = A.shape[1]
         Rp = K.round_rank(R)
-        a_pad, a_t = pad_cast(A, Rp)
-        b_pad, b_t = pad_cast(Bf, Rp)
+        a_ext, a_t2 = K.factor_operands(A, Rp)
+        b_ext, b_t2 = K.factor_operands(Bf, Rp)
         cs_pad = torch.nn.functional.pad(cs.detach().to(F32), (0, Rp - R)).contiguous()
-        return AdapterOperands(a_pad, a_t, b_pad, b_t, cs_pad, R)
-
-
-def pad_cast(F, Rp):
-    """fp32 [rows,R] -> (bf16 [rows,Rp] zero padded, bf16 [Rp,rows])."""
-    Fp = torch.nn.functional.pad(F.detach(), (0, Rp - F.shape[1])).to(BF16).contiguous()
-    return Fp, Fp.t().contiguous()
+        return AdapterOperands(a_ext, a_t2, b_ext, b_t2, cs_pad, R)
 
 
 def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True):
     T = U = None
     if ops is not None:
-        T, U = K.adapter_rows_fwd(x, ops.a_t, ops.cs_pad)
-        y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_pad, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
+        T, U = K.adapter_rows_fwd(x, ops.a_t2, ops.cs_pad)
+        y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_ext, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
     else:
         y = K.gemm_cp(x, fz.w, bias=bias_eff, epi=epi, want_pre=want_pre)
     return y, T, U
@@ -83,10 +79,10 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None):
         dx = K.gemm_cp(G, fz.wt, epi=epi, aux=dgelu_aux) if need_dx else None
         return dx, None, None, None, None
     R = ops.rank
-    dT, dcs = K.adapter_rows_bwd(G, ops.b_t, ops.cs_pad, T)
+    dT, dcs = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T)
     dx = None
     if need_dx:
-        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_pad, ext_slices=1, epi=epi, aux=dgelu_aux)
+        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux)
     dA, _ = K.adapter_cols(x, dT, 1, ops.rp)
     dB, colsum = K.adapter_cols(G, U, ops.slices, ops.rp, want_colsum=need_bias)
     return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum

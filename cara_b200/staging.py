@@ -25,11 +25,6 @@ class Terms:
         self.A, self.cs, self.B, self.bias, self.ops = A, cs, B, bias, ops
 
 
-def _pad_cast(F, Rp):
-    Fp = torch.nn.functional.pad(F.detach(), (0, Rp - F.shape[-1])).to(BF16).contiguous()
-    return Fp, Fp.transpose(-1, -2).contiguous()
-
-
 def _modules(model):
     from .vit import Attention, Mlp
     attn = [m for m in model.modules() if isinstance(m, Attention) and hasattr(m, "attn_idx")]
@@ -49,8 +44,6 @@ def staged(model):
     if cache is not None and cache[0] == key:
         return cache[1], cache[2]
     dev = P["CP_A1"].device
-    if dev.type != "cuda":
-        raise RuntimeError("cara_b200: the adapted model must live on a CUDA device")
     R = P["CP_A1"].shape[1]
     Rp = K.round_rank(R)
     if R > 32:
@@ -76,11 +69,11 @@ def staged(model):
     b_fc2 = torch.stack([m.fc2.bias.detach().float() for m in mlp]) + s_m.view(Lm, 1) * f["CP_bias3"]
 
     with torch.no_grad():
-        a2_pad, a2_t = _pad_cast(f["CP_A2"], Rp)
-        kr_pad, kr_t = _pad_cast(kr_attn, Rp)
-        p2_pad, p2_t = _pad_cast(f["CP_P2"], Rp)
-        p3_pad, p3_t = _pad_cast(f["CP_P3"], Rp)
-        afc2_pad, afc2_t = _pad_cast(a_fc2, Rp)
+        a2_pad, a2_t = K.factor_operands(f["CP_A2"], Rp)
+        kr_pad, kr_t = K.factor_operands(kr_attn, Rp)
+        p2_pad, p2_t = K.factor_operands(f["CP_P2"], Rp)
+        p3_pad, p3_t = K.factor_operands(f["CP_P3"], Rp)
+        afc2_pad, afc2_t = K.factor_operands(a_fc2, Rp)
         pad = lambda t: torch.nn.functional.pad(t.detach(), (0, Rp - R)).contiguous()  # noqa: E731
         csq, csp, cs1, cs2 = pad(cs_qkv), pad(cs_proj), pad(cs_fc1), pad(cs_fc2)
 

@@ -1,0 +1,116 @@
+"""Training-step plumbing around the kernels: flat trainable buffer, fused AdamW, LR schedule, data-parallel
+gradient exchange.
+
+The reference's step is vit_cp.py:45-50 (forward, CE, zero_grad, backward, AdamW over ``CP*`` + ``head``
+with lr 1e-3 / wd 1e-4, vit_cp.py:176-187).  Here the ~120 k trainable scalars live in ONE flat fp32 buffer
+(parameters and ``.grad`` are views into it) so that the optimizer is one fused kernel launch and the
+data-parallel exchange is one NCCL all-reduce of <= 1.1 MB per step; the frozen backbone is
+replicated and never communicated.
+"""
+import math
+
+import torch
+
+from . import kernels as K
+
+
+def freeze_backbone(model):
+    """vit_cp.py:176-182: trainable iff the parameter name contains "CP" or "head"."""
+    trainable = []
+    for n, p in model.named_parameters():
+        if "CP" in n or "head" in n:
+            p.requires_grad = True
+            trainable.append((n, p))
+        else:
+            p.requires_grad = False
+    return trainable
+
+
+class FlatTrainable:
+    """Re-homes the trainable parameters into one contiguous fp32 buffer (and their grads into another)."""
+
+    def __init__(self, named_params):
+        self.named = list(named_params)
+        total = sum(p.numel() for _, p in self.named)
+        dev = self.named[0][1].device
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.slices = {}
+        off = 0
+        for n, p in self.named:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            self.slices[n] = (off, off + k)
+            off += k
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for _, p in self.named:           # re-attach if someone set grads to None
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or \
+               p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
+                a, b = self.slices[_]
+                p.grad = self.grad[a:b].view(p.shape)
+
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+
+class FusedAdamW:
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction) as one kernel over the flat buffer."""
+
+    def __init__(self, flat: FlatTrainable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+        self.flat = flat
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(flat.flat)
+        self.v = torch.zeros_like(flat.flat)
+        self.t = 0
+        self.param_groups = [{"lr": lr}]   # scheduler-facing, like torch.optim
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_grad()
+
+    def step(self, grad_scale=1.0):
+        self.t += 1
+        lr = self.param_groups[0]["lr"]
+        K.adamw_step(self.flat.flat, self.flat.grad, self.m, self.v, lr, self.t, self.betas, self.eps,
+                     self.weight_decay, gscale=grad_scale)
+
+
+def cosine_lr(epoch, base_lr=1e-3, t_initial=100, warmup_t=10, lr_min=1e-5, warmup_lr_init=1e-6, decay_rate=0.1):
+    """timm ``CosineLRScheduler(t_initial=100, warmup_t=10, lr_min=1e-5, warmup_lr_init=1e-6, decay_rate=0.1)``
+    evaluated at an epoch index, as vit_cp.py:55-56,187 steps it (cycle_limit 1, no warmup prefix)."""
+    if epoch < warmup_t:
+        return warmup_lr_init + epoch * (base_lr - warmup_lr_init) / warmup_t
+    i = epoch // t_initial
+    if i >= 1:
+        return lr_min
+    lr_max = base_lr * (decay_rate ** i)
+    return lr_min + 0.5 * (lr_max - lr_min) * (1.0 + math.cos(math.pi * (epoch - t_initial * i) / t_initial))
+
+
+def allreduce_grads(flat: FlatTrainable, world_size):
+    """One in-place sum all-reduce of the flat CP+head gradient (NCCL over NVLink on GPUs, gloo in CPU tests);
+    the 1/world_size of the global-batch mean is applied inside the fused AdamW kernel (grad_scale)."""
+    if world_size > 1:
+        torch.distributed.all_reduce(flat.grad, op=torch.distributed.ReduceOp.SUM)
+
+
+def shard_batch(global_batch, rank, world_size):
+    """Contiguous even split of the global batch over the ranks (frozen backbone replicated)."""
+    if global_batch % world_size != 0:
+        raise ValueError("global batch %d is not divisible by world size %d" % (global_batch, world_size))
+    per = global_batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+def train_step(model, opt, x, y, world_size=1):
+    """One vit_cp.py:45-50 iteration on this rank's shard; returns the (local) loss tensor."""
+    out = model(x)
+    loss = torch.nn.functional.cross_entropy(out, y)
+    opt.zero_grad()
+    loss.backward()
+    allreduce_grads(opt.flat, world_size)
+    opt.step(grad_scale=1.0 / world_size)
+    return loss

@@ -1,0 +1,143 @@
+"""Fine-tune / evaluate ViT + CaRA on VTAB-1k -- the reference's entry point on the B200 kernels.
+
+Usage (as in the reference README, from the repo root):
+    PYTHONPATH=. python image_classification/vit_cp.py --dataset=cifar --dim=16
+    PYTHONPATH=. python image_classification/vit_cp.py --dataset=cifar --dim=16 --evaluate=ckpt.pt
+
+Flags ``--dim --lr --dataset --evaluate --model`` are the reference's (vit_cp.py:85-116); the step semantics are
+its loop body (vit_cp.py:45-50): forward, cross-entropy, backward, AdamW(lr, wd=1e-4) over ``CP*`` + ``head``,
+cosine schedule stepped with the epoch index (vit_cp.py:55-56,187), test every 10 epochs and keep the best
+checkpoint (vit_cp.py:57-68).  Additive flags: ``--epochs``, ``--batch-size``, ``--synthetic`` (VTAB-shaped
+random data when ./data/vtab-1k is absent), ``--no-merge`` (evaluate through the adapter kernels instead of
+folding the CP delta into the frozen weights first).  Multi-GPU: launch with torchrun; the batch is sharded
+over the ranks and only the flat CP+head gradient (<= 1.1 MB) is all-reduced.
+"""
+import os
+import random
+import sys
+from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
+
+import numpy as np
+import torch as th
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from vtab import get_classes_num, get_data  # noqa: E402
+from vtab_config import config  # noqa: E402
+
+from cara_b200 import train as T  # noqa: E402
+from cara_b200.merge import merge_cara  # noqa: E402
+from cara_b200.vit import create_model  # noqa: E402
+from src.cara.cara import cara  # noqa: E402
+
+
+@th.no_grad()
+def test(model, dl):
+    """Top-1 accuracy (reference vit_cp.py:73-82; avalanche's Accuracy replaced by a running mean)."""
+    model.eval()
+    correct = total = 0
+    for x, y in dl:
+        x, y = x.cuda(non_blocking=True), y.cuda(non_blocking=True)
+        correct += int((model(x).argmax(dim=1).view(-1) == y).sum())
+        total += int(y.numel())
+    return correct / max(total, 1)
+
+
+def train(args, model, dl, tdl, opt, epochs, world_size=1, rank=0):
+    """Reference vit_cp.py:19-70."""
+    model.train()
+    acc, old_name, use_sched = 0.0, None, True
+    for epoch in range(epochs):
+        for x, y in dl:
+            x, y = x.cuda(non_blocking=True), y.cuda(non_blocking=True)
+            if world_size > 1:
+                lo, hi = T.shard_batch(x.shape[0], rank, world_size)
+                x, y = x[lo:hi], y[lo:hi]
+            loss = T.train_step(model, opt, x, y, world_size)
+            if use_sched:
+                opt.param_groups[0]["lr"] = T.cosine_lr(epoch, base_lr=args.lr)
+        if rank == 0:
+            print(f"e: {epoch}, l: {round(float(loss), 7)}, a:{acc}", flush=True)
+        if epoch % 10 == 0 and epoch != 0:
+            if epoch >= 50:
+                use_sched = False
+            acc = test(model, tdl)
+            model.train()
+            if acc > args.best_acc and rank == 0:
+                args.best_acc = acc
+                if old_name is not None:
+                    os.remove(old_name)
+                old_name = f"./vit_{args.dataset}_{round(acc, 5)}_seed_{args.seed}.pt"
+                th.save(model.state_dict(), old_name)
+    return model, old_name
+
+
+def _parse_args():
+    p = ArgumentParser(formatter_class=ArgumentDefaultsHelpFormatter)
+    p.add_argument("--dim", default=32, type=int, help="Number of trainable ranks.")
+    p.add_argument("--lr", default=1e-3, type=float, help="Learning rate")
+    p.add_argument("--dataset", default="svhn", type=str, choices=sorted(config), help="Dataset to train")
+    p.add_argument("--evaluate", default=None, type=str, help="Evalute model only")
+    p.add_argument("--model", type=str, default="vit_base_patch16_224_in21k")
+    p.add_argument("--epochs", type=int, default=100)
+    p.add_argument("--batch-size", type=int, default=64, help="global train batch")
+    p.add_argument("--synthetic", action="store_true", help="force VTAB-shaped synthetic data")
+    p.add_argument("--no-merge", action="store_true", help="evaluate without folding the CP delta into W")
+    return p.parse_args()
+
+
+def main(sd=None):
+    args = _parse_args()
+    print(args)
+    name = args.dataset
+    data_config = config[name]
+    seed = data_config["seed"] if sd is None else sd
+    scale = data_config["scale"]
+    args.best_acc = 0.0
+    args.seed = seed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    th.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        th.distributed.init_process_group("nccl")
+    print(f"\n\nSeed: {seed}")
+    np.random.seed(seed)
+    random.seed(seed)
+    th.manual_seed(seed)
+    th.cuda.manual_seed_all(seed)
+
+    train_dl, test_dl = get_data(name, evaluate=True, batch_size=args.batch_size,
+                                 synthetic=True if args.synthetic else None)
+    num_classes = get_classes_num(name)
+    vit = create_model(args.model, checkpoint_path="./ViT-B_16.npz", drop_path_rate=0.1)
+    vit = cara({"model": vit, "rank": args.dim, "scale": scale, "l_mu": data_config["init_mean"],
+                "l_std": data_config["init_std"]})
+    vit.reset_classifier(num_classes)
+    vit = vit.cuda()
+
+    if args.evaluate is not None:
+        print("Only evaluation")
+        vit.load_state_dict(th.load(args.evaluate, map_location="cuda"))
+        if not args.no_merge:
+            merge_cara(vit)
+        acc = test(vit, test_dl)
+        print(f"Accuracy: {acc}")
+        sys.exit(0)
+
+    trainable = T.freeze_backbone(vit)
+    print(f"Total parameters: {sum(p.numel() for n, p in trainable if 'head' not in n)}")
+    print(vit.head)
+    opt = T.FusedAdamW(T.FlatTrainable(trainable), lr=args.lr, weight_decay=1e-4)
+    vit, old_name = train(args, vit, train_dl, test_dl, opt, args.epochs, world, rank)
+    print("\n\n Evaluating....")
+    acc = test(vit, test_dl)
+    print(acc)
+    if acc > args.best_acc and rank == 0:
+        args.best_acc = acc
+        if old_name is not None:
+            os.remove(old_name)
+        th.save(vit.state_dict(), f"./vit_{name}_{round(args.best_acc, 5)}_seed_{seed}.pt")
+    print(f"Accuracy: {args.best_acc}")
+
+
+if __name__ == "__main__":
+    main()

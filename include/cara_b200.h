@@ -68,20 +68,25 @@ CARA_API int cara_ln_bwd(const void* dh, const float* x, const float* mean, cons
                          const float* dx_in, float* dx_out, void* g_out, const float* rowscale, int rows_per_sample,
                          int M, int C, int act_fp32, void* stream);
 
-/* Rank-R side chain, forward:  T = X A (fp32 [M,Rp]);  Uhat[:, s*Rp:(s+1)*Rp] = scales[s] (.) T.
- * X bf16 [M,K]; At = A^T bf16 [Rp,K] (rank zero-padded to Rp in {16,32}); scales fp32 [slices,Rp]. */
-CARA_API int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At, const float* scales,
+/* Rank-R side chain.  Precision convention: factor matrices and low-rank activations are bf16 (hi, lo) pairs
+ * (x = hi + lo).  A transposed factor operand "Ft2" is bf16 [2*Rp, K] = [hi rows ; lo rows]; a low-rank
+ * activation block is bf16 [.., 3*Rp] = [hi | lo | hi], to be multiplied in cara_gemm_cp (K1 = 3*Rp) against
+ * an out-side factor laid out [hi | hi | lo].  Rp = rank zero-padded to 16 or 32.
+ *
+ * Forward:  T = X A (fp32 [M,Rp]);  Uhat[:, s*3Rp : (s+1)*3Rp] = split(scales[s] (.) T).
+ * X bf16 [M,K] (K % 64 == 0); At2 = split(A)^T; scales fp32 [slices,Rp]. */
+CARA_API int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At2, const float* scales,
                                    int slices, int Rp, float* T, void* Uhat, void* stream);
 /* Backward of the same chain: per output slice s, dU_s = G[:, s*w:(s+1)*w] B;
- *   dThat = sum_s scales[s] (.) dU_s  (bf16 [M,Rp]);  dscales[s] += sum_m dU_s (.) T  (fp32, accumulated).
- * G bf16 [M,N]; Bt = B^T bf16 [Rp, N/slices]. */
-CARA_API int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int slices, const void* Bt,
+ *   dThat = split(sum_s scales[s] (.) dU_s)  (bf16 [M,3Rp]);  dscales[s] += sum_m dU_s (.) T  (fp32, accumulated).
+ * G bf16 [M,N]; Bt2 = split(B)^T bf16 [2Rp, N/slices]. */
+CARA_API int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int slices, const void* Bt2,
                                    const float* scales, int Rp, const float* T, void* dThat, float* dscales,
                                    void* stream);
 /* Factor gradients as skinny contractions over the M tokens (no dW is formed):
- *   out[k mod w, :] += sum_m X[m,k] V[m, (k/w)*Rp : +Rp]   (w = Kc/slices);  colsum[k] += sum_m X[m,k].
- * X bf16 [M,Kc] (Kc % 256 == 0), V bf16 [M, slices*Rp]; out fp32 [w,Rp] and colsum fp32 [Kc] are
- * accumulated into (caller zeroes them). */
+ *   out[k mod w, :] += sum_m X[m,k] (Vhi + Vlo)[m, slice k/w]   (w = Kc/slices);  colsum[k] += sum_m X[m,k].
+ * X bf16 [M,Kc] (Kc % 256 == 0), V bf16 [M, slices*3Rp] in the [hi | lo | hi] layout; out fp32 [w,Rp] and
+ * colsum fp32 [Kc] are accumulated into (caller zeroes them). */
 CARA_API int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, long ldv, int slices, int Rp,
                                float* out, float* colsum, void* stream);
 

@@ -1,0 +1,108 @@
+"""CPU tests of the host-side logic: C-ABI exports, factor staging vs. the oracle's factoring, checkpoint
+schema round trip with the oracle's state, launcher argument checks."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import cara_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    import ctypes
+    from cara_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "cara_b200.h")).read()
+    declared = sorted(set(re.findall(r"CARA_API\s+[\w\s\*]+?\b(cara_\w+)\s*\(", hdr)))
+    assert len(declared) >= 16
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(L.exported_symbols()) == declared
+    assert L.lib().cara_abi_version() == 1
+
+
+def _small():
+    from cara_b200.vit import create_model
+    from src.cara.cara import cara
+    g = O.Geometry(embed_dim=256, depth=2, num_heads=4, rank=8, num_classes=7)
+    vit = create_model("vit_base_patch16_224_in21k", depth=2, embed_dim=256, num_heads=4)
+    vit = cara({"model": vit, "rank": 8, "scale": 2.5, "l_mu": 1.0, "l_std": 0.0})
+    vit.reset_classifier(7)
+    st = O.synthetic_state(g, dtype=torch.float32)
+    vit.load_state_dict(st, strict=True)
+    return vit, st, g
+
+
+def test_staging_matches_oracle_factoring_and_grad_chain():
+    """staged (A, cs, B, bias) == oracle.adapter_terms (A.1) and autograd through the staging reproduces the
+    oracle's chain rule to the CP parameters (A.2)."""
+    from cara_b200 import staging
+    vit, st, g = _small()
+    amap, mmap = staging.staged(vit)
+    s = 2.5
+    torch.manual_seed(0)
+    total = 0.0
+    ref_total = 0.0
+    leaves = {k: st[k].clone().requires_grad_(True) for k in st if k.startswith("CP_")}
+    work = dict(st); work.update(leaves)
+    for l, blk in enumerate(vit.blocks):
+        for which, t in (("qkv", amap[id(blk.attn)][0]), ("proj", amap[id(blk.attn)][1]),
+                         ("fc1", mmap[id(blk.mlp)][0]), ("fc2", mmap[id(blk.mlp)][1])):
+            A, c, B, beta = O.adapter_terms(work, g, l, which)
+            assert torch.allclose(t.A, A.detach(), atol=1e-6) and torch.allclose(t.B, B.detach(), atol=1e-6)
+            assert torch.allclose(t.cs, (s * c).detach(), atol=1e-6), which
+            assert t.ops.cs_pad.shape == (c.shape[0], 16) and t.ops.a_t2.shape == (32, A.shape[0])
+            hi = A.detach().bfloat16()
+            assert torch.equal(t.ops.a_ext[:, :8], hi) and torch.equal(t.ops.a_ext[:, 16:24], hi)
+            assert torch.equal(t.ops.a_ext[:, 32:40], (A.detach() - hi.float()).bfloat16())
+            assert float(t.ops.a_ext[:, 8:16].abs().max()) == 0 and torch.equal(t.ops.a_t2[:16].t(), t.ops.a_ext[:, :16])
+            recon = t.ops.a_ext[:, :8].float() + t.ops.a_ext[:, 32:40].float()
+            assert float((recon - A.detach()).abs().max()) <= float(A.detach().abs().max()) * 2.0 ** -15
+            wa, wc, wb = torch.randn_like(A), torch.randn_like(c), torch.randn_like(B)
+            total = total + (t.A * wa).sum() + (t.cs * wc).sum() + (t.B * wb).sum()
+            ref_total = ref_total + (A * wa).sum() + (s * c * wc).sum() + (B * wb).sum()
+            if beta is not None:
+                key = {"proj": "attn.proj", "fc1": "mlp.fc1", "fc2": "mlp.fc2"}[which]
+                assert torch.allclose(t.bias, (st["blocks.%d.%s.bias" % (l, key)] + s * beta).detach(), atol=1e-6)
+                wbias = torch.randn_like(beta)
+                total = total + (t.bias * wbias).sum(); ref_total = ref_total + (s * beta * wbias).sum()
+    total.backward(); ref_total.backward()
+    for k, leaf in leaves.items():
+        got = getattr(vit, k).grad
+        assert torch.allclose(got, leaf.grad, rtol=1e-4, atol=1e-5), k
+    # cache: same objects until a parameter changes
+    again, _ = staging.staged(vit)
+    assert again is amap
+    with torch.no_grad():
+        vit.CP_R1.add_(1.0)
+    assert staging.staged(vit)[0] is not amap
+
+
+def test_state_dict_schema_roundtrip():
+    vit, st, g = _small()
+    sd = vit.state_dict()
+    assert set(sd) == set(st)
+    for k in st:
+        assert tuple(sd[k].shape) == tuple(st[k].shape), k
+    assert set(O.cp_shapes(g)) | set(O.backbone_shapes(g)) == set(sd)
+
+
+def test_kernel_wrappers_refuse_cpu_tensors():
+    from cara_b200 import kernels as K
+    from cara_b200._lib import CaraLibraryError
+    with pytest.raises(CaraLibraryError):
+        K.gemm_cp(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(256, 64, dtype=torch.bfloat16))
+    with pytest.raises(CaraLibraryError):
+        K.ln_fwd(torch.zeros(8, 128), torch.ones(128), torch.zeros(128))
+
+
+def test_vtab_config_and_cli_surface():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vtab_config", os.path.join(ROOT, "image_classification", "vtab_config.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    assert len(mod.config) == 19
+    for name, c in mod.config.items():
+        assert set(c) == {"init_mean", "init_std", "scale", "seed", "logger"}, name

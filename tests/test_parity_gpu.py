@@ -149,3 +149,40 @@ def test_reference_forward_shape():
         warnings.simplefilter("ignore")
         out = vit(torch.randn((2, 3, 224, 224)).cuda())
     assert tuple(out.shape) == (2, 21843)
+
+
+def test_eval_merge_matches_adapter_path_and_oracle():
+    """SURVEY A.3 / BASELINE config 5: folding the CP delta into the frozen weights gives the same logits as the
+    adapter kernels and as the oracle's materialised merge."""
+    from cara_b200.merge import merge_cara
+    g = O.Geometry(depth=3, rank=16, num_classes=10)
+    vit, st = build(g, 2.5)
+    vit.eval()
+    x, _ = O.synthetic_batch(g, 4)
+    with torch.no_grad():
+        y_adapter = vit(x.cuda()).cpu()
+        assert merge_cara(vit) == 4 * g.depth
+        y_merged = vit(x.cuda()).cpu()
+    ref = O.forward_plain(O.merged_weights(st, g, 2.5), g, x)
+    assert rel(y_merged, ref) <= 1e-2 and rel(y_adapter, ref) <= 1e-2
+    assert rel(y_merged, y_adapter) <= 1e-2
+
+
+def test_fused_adamw_step_matches_oracle_update():
+    """One full vit_cp.py:45-50 step: parameters after the fused AdamW equal the oracle's AdamW applied to the
+    CUDA path's gradients, and stay close to the oracle's own step."""
+    from cara_b200 import train as T
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    vit, st = build(g, 1.0)
+    vit.eval()
+    opt = T.FusedAdamW(T.FlatTrainable(T.freeze_backbone(vit)), lr=1e-3, weight_decay=1e-4)
+    x, y = O.synthetic_batch(g, 2)
+    before = {n: p.detach().cpu().clone() for n, p in vit.named_parameters() if p.requires_grad}
+    loss = T.train_step(vit, opt, x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    for n, p in vit.named_parameters():
+        if p.requires_grad:
+            gr = p.grad.detach().cpu()
+            want, _, _ = O.adamw_update(before[n], gr, torch.zeros_like(gr), torch.zeros_like(gr), 1)
+            assert rel(p.detach().cpu(), want) < 1e-6, n
+    assert abs(float(loss) - float(O.loss_and_grads(st, g, x, y, 1.0)[1])) < 3e-2
