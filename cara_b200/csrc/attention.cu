@@ -8,8 +8,8 @@
 //
 // Math: warp-level mma.sync m16n8k16 bf16 with fp32 accumulation, flash-style online softmax over
 // 64-key chunks (exp2 with pre-scaled logits), fp32 softmax statistics.  Backward is two passes over
-// the head held in shared memory (warps own query tiles for dQ, then key tiles for dK/dV) so no
-// atomics are needed.  Attention is ~6 % of the step's FLOPs.
+// the head held in shared memory (warps own query tiles for delta + dQ, then key tiles for dK/dV) so no
+// atomics are needed; delta = rowsum(P (.) dP) is recomputed in-kernel instead of rowsum(dO (.) O).  Attention is ~6 % of the step's FLOPs.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -212,7 +212,6 @@ attn_bwd_kernel(const AttnArgs a) {
   const long pitch = 3L * C;
   const __nv_bfloat16* base = a.qkv + static_cast<long>(b) * N * pitch + h * D;
   const __nv_bfloat16* dob = a.d_o + static_cast<long>(b) * N * C + h * D;
-  const __nv_bfloat16* ob = a.o + static_cast<long>(b) * N * C + h * D;
   constexpr int TB = HeadTile<D>::PITCH;
   HeadTile<D> tq{s_u32(smem)}, tk{tq.base + npad * TB}, tv{tk.base + npad * TB}, tdo{tv.base + npad * TB};
   float* s_lse = reinterpret_cast<float*>(smem + 4 * npad * TB);
@@ -221,24 +220,9 @@ attn_bwd_kernel(const AttnArgs a) {
   load_head<D>(tk, base + C, pitch, N, npad, tid, 256);
   load_head<D>(tv, base + 2 * C, pitch, N, npad, tid, 256);
   load_head<D>(tdo, dob, C, N, npad, tid, 256);
-  // delta_i = sum_d dO[i,d] O[i,d]; lse padded with +big so padded queries get P = 0
+  // lse padded with +big so padded queries get P = 0 in pass 2
   const float* lse = a.lse + (static_cast<long>(b) * a.H + h) * N;
-  for (int row = warp; row < npad; row += NW) {
-    float acc = 0.f;
-    if (row < N) {
-      for (int d = lane * 2; d < D; d += 64) {
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + static_cast<long>(row) * C + d));
-        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + static_cast<long>(row) * C + d));
-        acc += x.x * y.x + x.y * y.y;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      s_delta[row] = acc;
-      s_lse[row] = row < N ? lse[row] : 1e30f;
-    }
-  }
+  for (int row = tid; row < npad; row += 256) s_lse[row] = row < N ? lse[row] : 1e30f;
   cp_async_commit_wait_all();
   __syncthreads();
 
@@ -253,7 +237,34 @@ attn_bwd_kernel(const AttnArgs a) {
     load_a_frags<D>(tdo, qt * 16, lane, dof);
     const int r_lo = qt * 16 + g, r_hi = r_lo + 8;
     const float lse_lo = s_lse[r_lo], lse_hi = s_lse[r_hi];
-    const float dl_lo = s_delta[r_lo], dl_hi = s_delta[r_hi];
+    // delta_i = sum_j P_ij dP_ij from the SAME recomputed P / dP that form dS below, so every row of dS sums to
+    // zero to fp32 accuracy.  (The usual rowsum(dO (.) O) inherits the bf16 rounding of the stored O, which for
+    // peaked softmax rows is the dominant dq/dk error.)
+    float dl_lo = 0.f, dl_hi = 0.f;
+    for (int k0 = 0; k0 < npad; k0 += KC) {
+      float s[KC / 8][4], dp[KC / 8][4];
+#pragma unroll
+      for (int j = 0; j < KC / 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+      }
+      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s);
+      mma_a_bt<D, KC / 8>(dof, tv, k0, lane, dp);
+#pragma unroll
+      for (int j = 0; j < KC / 8; ++j) {
+        const int key = k0 + j * 8 + 2 * t;
+        if (key < N) {
+          dl_lo = fmaf(exp2f(s[j][0] * sl2 - lse_lo), dp[j][0], dl_lo);
+          dl_hi = fmaf(exp2f(s[j][2] * sl2 - lse_hi), dp[j][2], dl_hi);
+        }
+        if (key + 1 < N) {
+          dl_lo = fmaf(exp2f(s[j][1] * sl2 - lse_lo), dp[j][1], dl_lo);
+          dl_hi = fmaf(exp2f(s[j][3] * sl2 - lse_hi), dp[j][3], dl_hi);
+        }
+      }
+    }
+    dl_lo = quad_sum(dl_lo); dl_hi = quad_sum(dl_hi);
+    if (t == 0) { s_delta[r_lo] = dl_lo; s_delta[r_hi] = dl_hi; }
     float dq[D / 8][4];
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
@@ -285,6 +296,10 @@ attn_bwd_kernel(const AttnArgs a) {
       if (r_hi < N) *reinterpret_cast<uint32_t*>(dq_base + static_cast<long>(r_hi) * pitch + col) = pack2(dq[j][2] * a.scale, dq[j][3] * a.scale);
     }
   }
+
+  // rows of s_delta past the last query tile are never written: zero them (their P is 0 anyway)
+  for (int row = ((N + 15) / 16) * 16 + tid; row < npad; row += 256) s_delta[row] = 0.f;
+  __syncthreads();
 
   // ---- pass 2: warps own 16-key tiles -> dK, dV (transposed score tiles: rows = keys, cols = queries)
   for (int kt = warp; kt * 16 < N; kt += NW) {

@@ -12,6 +12,7 @@ from . import _lib as L
 
 BF16, F32 = torch.bfloat16, torch.float32
 launch_count = 0  # number of cara_* kernel launches issued (bench.py reports it as gpu_launches)
+param_generation = 0  # bumped by adamw_step: parameters changed behind autograd's version counters
 gemm_events = None  # bench.py: list of (start event, end event, algorithmic flops) per fused-projection launch
 _dev = [None]
 
@@ -210,6 +211,8 @@ def merge_weights(W, A, Bf, cs):
 
 
 def adamw_step(p, g, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, gscale=1.0):
+    global param_generation
+    param_generation += 1
     st = _prep(p)
     assert p.dtype == F32 and p.is_contiguous() and g.is_contiguous()
     L.check(L.lib().cara_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0],

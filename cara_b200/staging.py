@@ -37,11 +37,15 @@ def staged(model):
     P = {n: getattr(model, n) for n in CP_NAMES}
     attn, mlp = _modules(model)
     frozen = [m.proj.bias for m in attn] + [m.fc1.bias for m in mlp] + [m.fc2.bias for m in mlp]
-    key = (tuple((p.data_ptr(), p._version) for p in P.values()), torch.is_grad_enabled(),
+    grad_on = torch.is_grad_enabled()
+    token = model.__dict__.get("_cara_fwd_token")
+    key = (tuple((p.data_ptr(), p._version) for p in P.values()), K.param_generation, grad_on,
            tuple(float(m.s) for m in attn + mlp), tuple((b.data_ptr(), b._version) for b in frozen),
            tuple(int(m.attn_idx) for m in attn), tuple(int(m.idx) for m in attn + mlp))
     cache = model.__dict__.get("_cara_stage")
-    if cache is not None and cache[0] == key:
+    # With autograd on, the staged tensors carry a graph that one backward consumes: share them only among the
+    # layers of ONE root forward (token set by VisionTransformer.forward_features); otherwise rebuild.
+    if cache is not None and cache[0] == key and (not grad_on or (token is not None and cache[3] is token)):
         return cache[1], cache[2]
     dev = P["CP_A1"].device
     R = P["CP_A1"].shape[1]
@@ -88,5 +92,5 @@ def staged(model):
         fc2 = Terms(a_fc2[i], cs_fc2[i], f["CP_P3"], b_fc2[i],
                     AdapterOperands(afc2_pad[i], afc2_t[i], p3_pad, p3_t, cs2[i], R))
         mmap[id(m)] = (fc1, fc2)
-    model.__dict__["_cara_stage"] = (key, amap, mmap)
+    model.__dict__["_cara_stage"] = (key, amap, mmap, token)
     return amap, mmap

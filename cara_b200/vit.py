@@ -235,6 +235,13 @@ class VisionTransformer(nn.Module):
         self.head = (nn.Linear(self.embed_dim, num_classes) if num_classes > 0 else nn.Identity()).to(dev)
 
     def forward_features(self, img):
+        self.__dict__["_cara_fwd_token"] = object()   # one staging of the CP factors per root forward
+        try:
+            return self._forward_features(img)
+        finally:
+            self.__dict__["_cara_fwd_token"] = None
+
+    def _forward_features(self, img):
         _require_cuda(img, "VisionTransformer.forward")
         if self.pos_drop.p:
             raise NotImplementedError("pos_drop > 0 is not part of the CaRA path (timm default 0)")
