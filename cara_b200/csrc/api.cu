@@ -92,13 +92,16 @@ int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, lon
   a.V = static_cast<const bf16*>(V); a.ldv = ldv; a.slice_w = Kc / slices; a.out = out; a.colsum = colsum;
   CARA_RET(cara::cols_launch(a, Rp, 0, CARA_STREAM(stream)), "cara_adapter_cols");
 }
-int cara_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int D, float scale, void* stream) {
-  cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(o), lse, nullptr, nullptr, B, N, H, D, scale};
+int cara_attn_fwd(const void* qkv, void* o, void* o_lo, float* lse, int B, int N, int H, int D, float scale,
+                  void* stream) {
+  cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(o), static_cast<bf16*>(o_lo), lse, nullptr,
+                   nullptr, B, N, H, D, scale};
   CARA_RET(cara::attn_fwd_launch(a, CARA_STREAM(stream)), "cara_attn_fwd");
 }
-int cara_attn_bwd(const void* qkv, const void* o, const float* lse, const void* d_o, void* dqkv, int B, int N, int H,
-                  int D, float scale, void* stream) {
-  cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(const_cast<void*>(o)), const_cast<float*>(lse),
+int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float* lse, const void* d_o, void* dqkv,
+                  int B, int N, int H, int D, float scale, void* stream) {
+  cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(const_cast<void*>(o)),
+                   static_cast<bf16*>(const_cast<void*>(o_lo)), const_cast<float*>(lse),
                    static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), B, N, H, D, scale};
   CARA_RET(cara::attn_bwd_launch(a, CARA_STREAM(stream)), "cara_attn_bwd");
 }

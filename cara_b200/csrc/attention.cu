@@ -9,7 +9,7 @@
 // Math: warp-level mma.sync m16n8k16 bf16 with fp32 accumulation, flash-style online softmax over
 // 64-key chunks (exp2 with pre-scaled logits), fp32 softmax statistics.  Backward is two passes over
 // the head held in shared memory (warps own query tiles for delta + dQ, then key tiles for dK/dV) so no
-// atomics are needed; delta = rowsum(P (.) dP) is recomputed in-kernel instead of rowsum(dO (.) O).  Attention is ~6 % of the step's FLOPs.
+// atomics are needed; delta = rowsum(dO (.) O) uses O kept as a bf16 (hi, lo) pair.  Attention is ~6 % of the step's FLOPs.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -83,14 +83,16 @@ __device__ __forceinline__ void load_a_frags(const HeadTile<D>& t, int row0, int
   for (int kk = 0; kk < D / 16; ++kk) ldsm_x4(t.at(row0 + (lane & 15), kk * 2 + (lane >> 4)), f[kk]);
 }
 
-// acc[j] (16 x 8 tiles, j over NT column tiles starting at row col0 of `t`) += A(16 x D) * t[col rows]^T
+// acc[j] (16 x 8 tiles, j over NT column tiles starting at row col0 of `t`) += A(16 x D) * t[col rows]^T;
+// only the first `ntp` 16-column pairs are computed (N is padded to 16, not to the chunk size)
 template <int D, int NT>
 __device__ __forceinline__ void mma_a_bt(const uint32_t (&af)[D / 16][4], const HeadTile<D>& t, int col0, int lane,
-                                         float (&acc)[NT][4]) {
+                                         float (&acc)[NT][4], int ntp) {
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
 #pragma unroll
     for (int jp = 0; jp < NT / 2; ++jp) {
+      if (jp >= ntp) continue;                      // warp-uniform: 16-column pairs past the padded length
       uint32_t bf[4];
       const int n = col0 + jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
       ldsm_x4(t.at(n, kk * 2 + ((lane >> 3) & 1)), bf);
@@ -103,10 +105,11 @@ __device__ __forceinline__ void mma_a_bt(const uint32_t (&af)[D / 16][4], const 
 // out[j] (16 x 8 tiles over D) += P(16 x 8*NT, fp32 accumulator layout, converted to bf16) * t[rows k0..]
 template <int D, int NT>
 __device__ __forceinline__ void mma_p_b(const float (&p)[NT][4], const HeadTile<D>& t, int k0, int lane,
-                                        float (&out)[D / 8][4]) {
+                                        float (&out)[D / 8][4], int ntp) {
   const int q = lane >> 3;
 #pragma unroll
   for (int ks = 0; ks < NT / 2; ++ks) {
+    if (ks >= ntp) continue;
     uint32_t af[4];
     af[0] = pack2(p[2 * ks][0], p[2 * ks][1]);
     af[1] = pack2(p[2 * ks][2], p[2 * ks][3]);
@@ -132,7 +135,7 @@ attn_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int N = a.N, npad = ((N + KC - 1) / KC) * KC;
+  const int N = a.N, npad = ((N + 15) / 16) * 16;
   const long pitch = 3L * a.H * D;
   const __nv_bfloat16* base = a.qkv + static_cast<long>(b) * N * pitch + h * D;
   HeadTile<D> tq{s_u32(smem)}, tk{tq.base + npad * HeadTile<D>::PITCH}, tv{tk.base + npad * HeadTile<D>::PITCH};
@@ -155,7 +158,8 @@ attn_fwd_kernel(const AttnArgs a) {
       float s[KC / 8][4];
 #pragma unroll
       for (int j = 0; j < KC / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s);
+      const int ntp = min(KC / 16, (npad - k0) / 16);
+      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s, ntp);
       float mx_lo = m_lo, mx_hi = m_hi;
 #pragma unroll
       for (int j = 0; j < KC / 8; ++j) {
@@ -179,17 +183,27 @@ attn_fwd_kernel(const AttnArgs a) {
         s[j][2] = exp2f(s[j][2] - m_hi); s[j][3] = exp2f(s[j][3] - m_hi);
         l_lo += s[j][0] + s[j][1]; l_hi += s[j][2] + s[j][3];
       }
-      mma_p_b<D, KC / 8>(s, tv, k0, lane, o);
+      mma_p_b<D, KC / 8>(s, tv, k0, lane, o, ntp);
     }
     l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
     const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
     const int r_lo = qt * 16 + g, r_hi = r_lo + 8;
-    __nv_bfloat16* orow = a.o + (static_cast<long>(b) * N) * (a.H * D) + h * D;
+    const long obase = (static_cast<long>(b) * N) * (a.H * D) + h * D;
+    // o (bf16) feeds the output projection; o_lo = bf16(o_fp32 - o) is kept for backward so that
+    // delta = rowsum(dO (.) O) is formed from a ~16-bit-mantissa O (see attn_bwd_kernel)
+    auto put = [&](int row, int col, float v0, float v1) {
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+      *reinterpret_cast<__nv_bfloat162*>(a.o + obase + static_cast<long>(row) * a.H * D + col) = hi;
+      if (a.o_lo != nullptr) {
+        const float2 hf = __bfloat1622float2(hi);
+        *reinterpret_cast<uint32_t*>(a.o_lo + obase + static_cast<long>(row) * a.H * D + col) = pack2(v0 - hf.x, v1 - hf.y);
+      }
+    };
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) {
       const int col = j * 8 + 2 * t;
-      if (r_lo < N) *reinterpret_cast<uint32_t*>(orow + static_cast<long>(r_lo) * a.H * D + col) = pack2(o[j][0] * i_lo, o[j][1] * i_lo);
-      if (r_hi < N) *reinterpret_cast<uint32_t*>(orow + static_cast<long>(r_hi) * a.H * D + col) = pack2(o[j][2] * i_hi, o[j][3] * i_hi);
+      if (r_lo < N) put(r_lo, col, o[j][0] * i_lo, o[j][1] * i_lo);
+      if (r_hi < N) put(r_hi, col, o[j][2] * i_hi, o[j][3] * i_hi);
     }
     if (a.lse != nullptr && t == 0) {
       float* lse = a.lse + (static_cast<long>(b) * a.H + h) * N;
@@ -207,22 +221,43 @@ attn_bwd_kernel(const AttnArgs a) {
   constexpr int NW = 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int N = a.N, npad = ((N + KC - 1) / KC) * KC;
+  const int N = a.N, npad = ((N + 15) / 16) * 16, nstat = ((N + 31) / 32) * 32;
   const int C = a.H * D;
   const long pitch = 3L * C;
   const __nv_bfloat16* base = a.qkv + static_cast<long>(b) * N * pitch + h * D;
   const __nv_bfloat16* dob = a.d_o + static_cast<long>(b) * N * C + h * D;
+  const __nv_bfloat16* ob = a.o + static_cast<long>(b) * N * C + h * D;
+  const __nv_bfloat16* olb = a.o_lo + static_cast<long>(b) * N * C + h * D;
   constexpr int TB = HeadTile<D>::PITCH;
   HeadTile<D> tq{s_u32(smem)}, tk{tq.base + npad * TB}, tv{tk.base + npad * TB}, tdo{tv.base + npad * TB};
   float* s_lse = reinterpret_cast<float*>(smem + 4 * npad * TB);
-  float* s_delta = s_lse + npad;
+  float* s_delta = s_lse + nstat;
   load_head<D>(tq, base, pitch, N, npad, tid, 256);
   load_head<D>(tk, base + C, pitch, N, npad, tid, 256);
   load_head<D>(tv, base + 2 * C, pitch, N, npad, tid, 256);
   load_head<D>(tdo, dob, C, N, npad, tid, 256);
-  // lse padded with +big so padded queries get P = 0 in pass 2
+  // delta_i = sum_d dO[i,d] (O + O_lo)[i,d]: O carried as a bf16 (hi, lo) pair, because with the plain bf16 O
+  // the rounding of O is the dominant dq/dk error for peaked softmax rows (rows of dS no longer sum to ~0).
+  // lse padded with +big so padded queries get P = 0 in pass 2.
   const float* lse = a.lse + (static_cast<long>(b) * a.H + h) * N;
-  for (int row = tid; row < npad; row += 256) s_lse[row] = row < N ? lse[row] : 1e30f;
+  for (int row = warp; row < nstat; row += NW) {
+    float acc = 0.f;
+    if (row < N) {
+      for (int d = lane * 2; d < D; d += 64) {
+        const long off = static_cast<long>(row) * C + d;
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + off));
+        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + off));
+        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(olb + off));
+        acc += x.x * (y.x + z.x) + x.y * (y.y + z.y);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      s_delta[row] = acc;
+      s_lse[row] = row < N ? lse[row] : 1e30f;
+    }
+  }
   cp_async_commit_wait_all();
   __syncthreads();
 
@@ -237,34 +272,7 @@ attn_bwd_kernel(const AttnArgs a) {
     load_a_frags<D>(tdo, qt * 16, lane, dof);
     const int r_lo = qt * 16 + g, r_hi = r_lo + 8;
     const float lse_lo = s_lse[r_lo], lse_hi = s_lse[r_hi];
-    // delta_i = sum_j P_ij dP_ij from the SAME recomputed P / dP that form dS below, so every row of dS sums to
-    // zero to fp32 accuracy.  (The usual rowsum(dO (.) O) inherits the bf16 rounding of the stored O, which for
-    // peaked softmax rows is the dominant dq/dk error.)
-    float dl_lo = 0.f, dl_hi = 0.f;
-    for (int k0 = 0; k0 < npad; k0 += KC) {
-      float s[KC / 8][4], dp[KC / 8][4];
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-      }
-      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s);
-      mma_a_bt<D, KC / 8>(dof, tv, k0, lane, dp);
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        const int key = k0 + j * 8 + 2 * t;
-        if (key < N) {
-          dl_lo = fmaf(exp2f(s[j][0] * sl2 - lse_lo), dp[j][0], dl_lo);
-          dl_hi = fmaf(exp2f(s[j][2] * sl2 - lse_hi), dp[j][2], dl_hi);
-        }
-        if (key + 1 < N) {
-          dl_lo = fmaf(exp2f(s[j][1] * sl2 - lse_lo), dp[j][1], dl_lo);
-          dl_hi = fmaf(exp2f(s[j][3] * sl2 - lse_hi), dp[j][3], dl_hi);
-        }
-      }
-    }
-    dl_lo = quad_sum(dl_lo); dl_hi = quad_sum(dl_hi);
-    if (t == 0) { s_delta[r_lo] = dl_lo; s_delta[r_hi] = dl_hi; }
+    const float dl_lo = s_delta[r_lo], dl_hi = s_delta[r_hi];
     float dq[D / 8][4];
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
@@ -275,8 +283,9 @@ attn_bwd_kernel(const AttnArgs a) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
         dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
       }
-      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s);
-      mma_a_bt<D, KC / 8>(dof, tv, k0, lane, dp);
+      const int ntp = min(KC / 16, (npad - k0) / 16);
+      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s, ntp);
+      mma_a_bt<D, KC / 8>(dof, tv, k0, lane, dp, ntp);
 #pragma unroll
       for (int j = 0; j < KC / 8; ++j) {
         const int key = k0 + j * 8 + 2 * t;
@@ -287,7 +296,7 @@ attn_bwd_kernel(const AttnArgs a) {
         s[j][0] = p0 * (dp[j][0] - dl_lo); s[j][1] = p1 * (dp[j][1] - dl_lo);
         s[j][2] = p2 * (dp[j][2] - dl_hi); s[j][3] = p3 * (dp[j][3] - dl_hi);
       }
-      mma_p_b<D, KC / 8>(s, tk, k0, lane, dq);
+      mma_p_b<D, KC / 8>(s, tk, k0, lane, dq, ntp);
     }
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) {
@@ -296,10 +305,6 @@ attn_bwd_kernel(const AttnArgs a) {
       if (r_hi < N) *reinterpret_cast<uint32_t*>(dq_base + static_cast<long>(r_hi) * pitch + col) = pack2(dq[j][2] * a.scale, dq[j][3] * a.scale);
     }
   }
-
-  // rows of s_delta past the last query tile are never written: zero them (their P is 0 anyway)
-  for (int row = ((N + 15) / 16) * 16 + tid; row < npad; row += 256) s_delta[row] = 0.f;
-  __syncthreads();
 
   // ---- pass 2: warps own 16-key tiles -> dK, dV (transposed score tiles: rows = keys, cols = queries)
   for (int kt = warp; kt * 16 < N; kt += NW) {
@@ -319,8 +324,9 @@ attn_bwd_kernel(const AttnArgs a) {
         st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
         dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
       }
-      mma_a_bt<D, QC / 8>(kf, tq, q0, lane, st);     // S^T = K Q^T
-      mma_a_bt<D, QC / 8>(vf, tdo, q0, lane, dpt);   // dP^T = V dO^T
+      const int ntp = min(QC / 16, (npad - q0) / 16);
+      mma_a_bt<D, QC / 8>(kf, tq, q0, lane, st, ntp);     // S^T = K Q^T
+      mma_a_bt<D, QC / 8>(vf, tdo, q0, lane, dpt, ntp);   // dP^T = V dO^T
 #pragma unroll
       for (int j = 0; j < QC / 8; ++j) {
         const int qi = q0 + j * 8 + 2 * t;
@@ -331,8 +337,8 @@ attn_bwd_kernel(const AttnArgs a) {
         dpt[j][2] = p2 * (dpt[j][2] - d0); dpt[j][3] = p3 * (dpt[j][3] - d1);
         st[j][0] = p0; st[j][1] = p1; st[j][2] = p2; st[j][3] = p3;
       }
-      mma_p_b<D, QC / 8>(st, tdo, q0, lane, dv);     // dV += P^T dO
-      mma_p_b<D, QC / 8>(dpt, tq, q0, lane, dk);     // dK += dS^T Q
+      mma_p_b<D, QC / 8>(st, tdo, q0, lane, dv, ntp);     // dV += P^T dO
+      mma_p_b<D, QC / 8>(dpt, tq, q0, lane, dk, ntp);     // dK += dS^T Q
     }
     const int r_lo = kt * 16 + g, r_hi = r_lo + 8;
 #pragma unroll
@@ -352,7 +358,7 @@ attn_bwd_kernel(const AttnArgs a) {
 
 template <int D>
 int fwd_t(const AttnArgs& a, cudaStream_t st) {
-  const int npad = ((a.N + KC - 1) / KC) * KC;
+  const int npad = ((a.N + 15) / 16) * 16;
   const int smem = 3 * npad * HeadTile<D>::PITCH;
   if (smem > 227 * 1024) return -51;
   static int configured = 0;
@@ -365,8 +371,8 @@ int fwd_t(const AttnArgs& a, cudaStream_t st) {
 }
 template <int D>
 int bwd_t(const AttnArgs& a, cudaStream_t st) {
-  const int npad = ((a.N + KC - 1) / KC) * KC;
-  const int smem = 4 * npad * HeadTile<D>::PITCH + 2 * npad * 4;
+  const int npad = ((a.N + 15) / 16) * 16, nstat = ((a.N + 31) / 32) * 32;
+  const int smem = 4 * npad * HeadTile<D>::PITCH + 2 * nstat * 4;
   if (smem > 227 * 1024) return -51;
   static int configured = 0;
   if (configured < smem) {
@@ -386,7 +392,7 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t st) {
   return -50;
 }
 int attn_bwd_launch(const AttnArgs& a, cudaStream_t st) {
-  if (a.B <= 0 || a.N <= 0 || a.H <= 0) return -50;
+  if (a.B <= 0 || a.N <= 0 || a.H <= 0 || a.o_lo == nullptr) return -50;
   if (a.D == 64) return bwd_t<64>(a, st);
   if (a.D == 80) return bwd_t<80>(a, st);
   return -50;

@@ -10,8 +10,11 @@
 // no second [M,N] pass exists.
 //
 // Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer + TMEM
-// owner, warps 2..5 = epilogue (TMEM -> registers -> global).  Two 256-column fp32 accumulators in
-// TMEM let the epilogue of tile i overlap the main loop of tile i+1.
+// owner, warps 2..5 = epilogue.  Two 256-column fp32 accumulators in TMEM let the epilogue of tile i
+// overlap the main loop of tile i+1.  Epilogue data path: tcgen05.ld -> registers (bias / GELU / GELU')
+// -> 128-byte-swizzled shared staging (conflict-free 16-byte stores) -> TMA tensor store, 32 rows x 64
+// columns per warp and step, double buffered; the GELU' operand arrives the same way through TMA loads
+// prefetched one step ahead.  HBM therefore only ever sees full 128-byte lines.
 #include "ptx.cuh"
 #include "gemm_sm100.h"
 #include "mathfn.cuh"
@@ -20,13 +23,19 @@ namespace cara {
 
 constexpr int BM = 128, BN = 256, BK = 64;      // CTA tile; BK*2B = one 128-byte swizzle row
 constexpr int UK = 16;                          // tcgen05 kind::f16 K per instruction
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES = BN * BK * 2;            // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int TMEM_COLS = 512;                  // 2 accumulators x 256 fp32 columns
 constexpr int NUM_THREADS = 192;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EC = 64;                          // epilogue step: 64 output columns = one 128-B swizzle row
+constexpr int EBUF = 32 * EC * 2;               // 4 KB staging buffer: 32 rows x 128 B
+// main-loop ring depth / staging tensors per epilogue kind (smem budget 227 KB)
+__host__ __device__ constexpr int num_stages(int epi) { return epi == EPI_NONE ? 4 : 3; }
+__host__ __device__ constexpr int num_stage_tensors(int epi) { return epi == EPI_NONE ? 1 : 2; }
+__host__ __device__ constexpr int gemm_smem(int epi) {
+  return num_stages(epi) * STAGE_BYTES + 4 * 2 * EBUF * num_stage_tensors(epi) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
 
 struct TileCoord {
   int m0, n0;
@@ -40,17 +49,22 @@ template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAux,
                const GemmArgs p) {
+  constexpr int STAGES = num_stages(EPI);
+  constexpr int NST = num_stage_tensors(EPI);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-B alignment
-  const uint32_t bars = tiles + STAGES * STAGE_BYTES;
-  // barrier map (8 B each): full[S], empty[S], tfull[2], tempty[2], then the TMEM base address word
+  const uint32_t stage_out = tiles + STAGES * STAGE_BYTES; // [4 warps][NST tensors][2 buffers][4 KB]
+  const uint32_t bars = stage_out + 4 * 2 * EBUF * NST;
+  // barrier map (8 B each): full[S], empty[S], tfull[2], tempty[2], aux[4 warps][2], then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  auto aux_bar = [&](int w, int b) { return bars + 8u * (2 * STAGES + 4 + w * 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 12);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -75,6 +89,12 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
     }
+    for (int w = 0; w < 4; ++w) {
+      mbar_init(aux_bar(w, 0), 1);
+      mbar_init(aux_bar(w, 1), 1);
+    }
+    tma_prefetch_desc(&mapOut);
+    if (EPI != EPI_NONE) tma_prefetch_desc(&mapAux);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -145,88 +165,111 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..5
     const int lg = warp & 3;                      // TMEM lane group this warp may touch
-    const int row = lg * 32 + lane;
+    const int ew = warp - 2;                      // staging slot of this warp
+    const uint32_t my_stage = stage_out + ew * (2 * EBUF * NST);   // tensor 0: [2][EBUF]; tensor 1: [2][EBUF]
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);          // 128-B swizzle phase of this thread's row
+    const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
     int as = 0;
     uint32_t aph = 0;
+    uint32_t q = 0;                               // running 64-column step counter (buffer / parity selector)
+    if (EPI == EPI_DGELU && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) {
+      const TileCoord t0 = tile_coord(blockIdx.x, p.tiles_n);
+      mbar_expect_tx(aux_bar(ew, 0), EBUF);
+      tma_load_2d(my_stage + 2 * EBUF, &mapAux, aux_bar(ew, 0), t0.n0, t0.m0 + lg * 32);
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord(t, p.tiles_n);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      const int m = tc.m0 + row;
-      const bool row_ok = m < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int n = tc.n0 + c * 32;
-        if (n < p.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      for (int c = 0; c < BN / EC; ++c, ++q) {
+        const uint32_t b = q & 1u;
+        const uint32_t so = my_stage + b * EBUF;                  // staging of the primary output
+        const uint32_t sx = my_stage + 2 * EBUF + b * EBUF;       // second tensor: GELU output / GELU' operand
+        // the TMA store that read this buffer two steps ago must have drained it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        if (EPI == EPI_DGELU) {
+          if (lane == 0) {                                        // prefetch the next step's operand tile
+            int nt = t, nc = c + 1;
+            if (nc == BN / EC) { nt = t + gridDim.x; nc = 0; }
+            if (nt < num_tiles) {
+              const TileCoord tn = tile_coord(nt, p.tiles_n);
+              mbar_expect_tx(aux_bar(ew, b ^ 1u), EBUF);
+              tma_load_2d(my_stage + 2 * EBUF + (b ^ 1u) * EBUF, &mapAux, aux_bar(ew, b ^ 1u), tn.n0 + nc * EC,
+                          tn.m0 + lg * 32);
             }
           }
-          if (row_ok) {
-            if (EPI == EPI_DGELU) {
-              // dX through GELU: multiply by gelu'(u), u = saved fc1 pre-activation
-              const uint4* u4 = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(m) * p.ldaux + n);
+          mbar_wait(aux_bar(ew, b), (q >> 1) & 1u);
+        }
+        uint32_t r[64];
+        tmem_ld32(t_row + c * EC, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld32(t_row + c * EC + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_wait();
+        const int n = tc.n0 + c * EC;
+        if (p.bias != nullptr && n < p.N) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(u4 + j);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 f = unpack_bf16(w[q]);
-                  v[8 * j + 2 * q + 0] *= gelu_grad_fast(f.x);
-                  v[8 * j + 2 * q + 1] *= gelu_grad_fast(f.y);
-                }
-              }
-            }
-            if (p.out != nullptr) {
-              uint4* o4 = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                o4[j] = o;
-              }
-            }
-            if (EPI == EPI_GELU) {
-              // fc1: `out` keeps the pre-activation for backward, `out2` gets GELU(u) for fc2.
-              // GELU is applied to the bf16-rounded pre-activation so fwd and bwd see the same u.
-              uint4* o4 = reinterpret_cast<uint4*>(p.out2 + static_cast<size_t>(m) * p.ldo2 + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float g[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  g[q] = gelu_fast(__bfloat162float(__float2bfloat16_rn(v[8 * j + q])));
-                uint4 o;
-                o.x = pack_bf16(g[0], g[1]);
-                o.y = pack_bf16(g[2], g[3]);
-                o.z = pack_bf16(g[4], g[5]);
-                o.w = pack_bf16(g[6], g[7]);
-                o4[j] = o;
-              }
-            }
+          for (int j = 0; j < 16; ++j) {
+            const float4 bv = __ldg(b4 + j);
+            r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + bv.x);
+            r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv.y);
+            r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv.z);
+            r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv.w);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                             // 8 x 16-byte chunks of this thread's row
+          const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+          if (EPI == EPI_DGELU) {
+            // dX through GELU: multiply by gelu'(u), u = saved fc1 pre-activation (TMA-staged, same swizzle)
+            uint32_t u0, u1, u2, u3;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(sx + off));
+            const uint32_t uw[4] = {u0, u1, u2, u3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16(uw[e]);
+              v[2 * e + 0] *= gelu_grad_fast(f.x);
+              v[2 * e + 1] *= gelu_grad_fast(f.y);
+            }
+          }
+          const uint32_t o0 = pack_bf16(v[0], v[1]), o1 = pack_bf16(v[2], v[3]);
+          const uint32_t o2 = pack_bf16(v[4], v[5]), o3 = pack_bf16(v[6], v[7]);
+          if (p.out != nullptr)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(so + off), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+          if (EPI == EPI_GELU) {
+            // fc1: `out` keeps the pre-activation for backward, `out2` gets GELU(u) for fc2.  GELU is applied
+            // to the bf16-rounded pre-activation so forward and backward see the same u.
+            const uint32_t ow[4] = {o0, o1, o2, o3};
+            uint32_t gw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16(ow[e]);
+              gw[e] = pack_bf16(gelu_fast(f.x), gelu_fast(f.y));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sx + off), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
+          }
+        }
+        if (c == BN / EC - 1) {                                   // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        fence_proxy_async();                                      // staging writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          if (p.out != nullptr) tma_store_2d(&mapOut, so, n, tc.m0 + lg * 32);
+          if (EPI == EPI_GELU) tma_store_2d(&mapAux, sx, n, tc.m0 + lg * 32);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
+    if (lane == 0) tma_store_wait<0>();                           // all output bytes are in global memory
   }
 
   tc_fence_before();
@@ -257,7 +300,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // Row-major bf16 [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-B swizzle.
-int make_map_bf16(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
+static int make_map_bf16(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return -1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) return -2;
@@ -273,20 +316,22 @@ int make_map_bf16(CUtensorMap* map, const void* base, long rows, long cols, long
 
 template <int EPI>
 static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
-                              const CUtensorMap& b1, const GemmArgs& args, int grid, cudaStream_t st) {
+                              const CUtensorMap& b1, const CUtensorMap& mo, const CUtensorMap& mx,
+                              const GemmArgs& args, int grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_cp_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_cp_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(EPI));
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  gemm_cp_kernel<EPI><<<grid, NUM_THREADS, GEMM_SMEM, st>>>(a0, b0, a1, b1, args);
+  gemm_cp_kernel<EPI><<<grid, NUM_THREADS, gemm_smem(EPI), st>>>(a0, b0, a1, b1, mo, mx, args);
   return cudaGetLastError();
 }
 
 int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
-  if (d.M <= 0 || d.N <= 0 || d.K0 <= 0 || (d.K0 % 8) != 0 || (d.N % 32) != 0) return -10;
-  CUtensorMap a0, b0, a1, b1;
+  if (d.M <= 0 || d.N <= 0 || d.K0 <= 0 || (d.K0 % 8) != 0 || (d.N % 64) != 0) return -10;
+  if (d.out == nullptr && d.epi != EPI_GELU) return -16;
+  CUtensorMap a0, b0, a1, b1, mo, mx;
   int rc;
   if ((rc = make_map_bf16(&a0, d.A0, d.M, d.K0, d.lda0, BM)) != 0) return rc * 10 - 1;
   if ((rc = make_map_bf16(&b0, d.B0, d.N, d.K0, d.ldb0, BN)) != 0) return rc * 10 - 2;
@@ -316,15 +361,24 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   const int num_tiles = args.tiles_m * args.tiles_n;
   int grid = d.num_sms > 0 ? d.num_sms : 148;
   if (grid > num_tiles) grid = num_tiles;
+  // epilogue tensors: 32-row x 64-column boxes (one per epilogue warp and step)
+  if (d.out != nullptr) {
+    if ((rc = make_map_bf16(&mo, d.out, d.M, d.N, d.ldo, 32)) != 0) return rc * 10 - 5;
+  } else {
+    mo = a0;
+  }
+  mx = a0;
   cudaError_t e;
   switch (d.epi) {
-    case EPI_NONE: e = launch_epi<EPI_NONE>(a0, b0, a1, b1, args, grid, st); break;
+    case EPI_NONE: e = launch_epi<EPI_NONE>(a0, b0, a1, b1, mo, mx, args, grid, st); break;
     case EPI_GELU:
       if (d.out2 == nullptr) return -13;
-      e = launch_epi<EPI_GELU>(a0, b0, a1, b1, args, grid, st); break;
+      if ((rc = make_map_bf16(&mx, d.out2, d.M, d.N, d.ldo2, 32)) != 0) return rc * 10 - 6;
+      e = launch_epi<EPI_GELU>(a0, b0, a1, b1, mo, mx, args, grid, st); break;
     case EPI_DGELU:
       if (d.aux == nullptr) return -14;
-      e = launch_epi<EPI_DGELU>(a0, b0, a1, b1, args, grid, st); break;
+      if ((rc = make_map_bf16(&mx, d.aux, d.M, d.N, d.ldaux, 32)) != 0) return rc * 10 - 7;
+      e = launch_epi<EPI_DGELU>(a0, b0, a1, b1, mo, mx, args, grid, st); break;
     default: return -15;
   }
   return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);

@@ -43,7 +43,7 @@ int cols_launch(const ColsArgs& a, int rp, int num_sms, cudaStream_t st);
 
 // Attention core (attention.cu): qkv [B, N, 3, H, D] -> o [B, N, H, D]
 struct AttnArgs {
-  const __nv_bfloat16* qkv; __nv_bfloat16* o; float* lse;       // lse [B, H, N] (log2 domain)
+  const __nv_bfloat16* qkv; __nv_bfloat16* o; __nv_bfloat16* o_lo; float* lse;   // lse [B, H, N] (log2 domain)
   const __nv_bfloat16* d_o; __nv_bfloat16* dqkv;                // backward only
   int B, N, H, D; float scale;
 };

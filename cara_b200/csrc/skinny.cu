@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------ rows_kernel
-constexpr int R_BM = 128, R_BK = 64, R_STAGES = 4;
+constexpr int R_BM = 128, R_BK = 64, R_STAGES = 3;   // 3 x 20 KB: three CTAs per SM => M = 50k tokens is one wave
 
 template <int RT, int CS>
 __global__ void __launch_bounds__(256)

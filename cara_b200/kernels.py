@@ -138,47 +138,54 @@ def adapter_rows_fwd(x, a_t2, scales):
     return T, U
 
 
-def adapter_rows_bwd(g, b_t2, scales, T):
-    """g bf16 [M,N]; b_t2 bf16 [2Rp,N/S]; scales [S,Rp]; T fp32 [M,Rp] -> (dThat bf16 [M,3Rp], dscales fp32 [S,Rp])."""
+def adapter_rows_bwd(g, b_t2, scales, T, dsc=None):
+    """g bf16 [M,N]; b_t2 bf16 [2Rp,N/S]; scales [S,Rp]; T fp32 [M,Rp] -> (dThat bf16 [M,3Rp], dscales fp32 [S,Rp]).
+    ``dsc`` (optional) is a pre-zeroed fp32 [S,Rp] buffer to accumulate into."""
     st = _prep(g)
     M, N = g.shape
     S, Rp = scales.shape
     assert b_t2.shape == (2 * Rp, N // S) and b_t2.is_contiguous() and T.shape == (M, Rp) and g.stride(1) == 1
     dT = torch.empty((M, 3 * Rp), device=g.device, dtype=BF16)
-    dsc = torch.zeros((S, Rp), device=g.device, dtype=F32)
+    if dsc is None:
+        dsc = torch.zeros((S, Rp), device=g.device, dtype=F32)
     L.check(L.lib().cara_adapter_rows_bwd(g.data_ptr(), g.stride(0), M, N, S, b_t2.data_ptr(), scales.data_ptr(), Rp,
                                           T.data_ptr(), dT.data_ptr(), dsc.data_ptr(), st), "cara_adapter_rows_bwd")
     return dT, dsc
 
 
-def adapter_cols(x, v, slices, Rp, want_colsum=False):
+def adapter_cols(x, v, slices, Rp, want_colsum=False, out=None, cs=None):
     """out [Kc/slices, Rp] = sum_s x[:, slice s]^T (vhi + vlo)[:, slice s]; v bf16 [M, slices*3Rp];
-    colsum [Kc] = column sums of x."""
+    colsum [Kc] = column sums of x.  ``out`` / ``cs`` (optional) are pre-zeroed buffers to accumulate into."""
     st = _prep(x)
     M, Kc = x.shape
     assert v.shape == (M, slices * 3 * Rp) and x.stride(1) == 1 and v.stride(1) == 1
-    out = torch.zeros((Kc // slices, Rp), device=x.device, dtype=F32)
-    cs = torch.zeros(Kc, device=x.device, dtype=F32) if want_colsum else None
+    if out is None:
+        out = torch.zeros((Kc // slices, Rp), device=x.device, dtype=F32)
+    if cs is None and want_colsum:
+        cs = torch.zeros(Kc, device=x.device, dtype=F32)
     L.check(L.lib().cara_adapter_cols(x.data_ptr(), x.stride(0), M, Kc, v.data_ptr(), v.stride(0), slices, Rp,
                                       out.data_ptr(), _p(cs), st), "cara_adapter_cols")
     return out, cs
 
 
-def attn_fwd(qkv, B, N, H, D, scale, want_lse=True):
+def attn_fwd(qkv, B, N, H, D, scale, train=True):
+    """-> (o bf16 [B*N, H*D], o_lo, lse); o_lo / lse are None when train is False."""
     st = _prep(qkv)
     assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.numel() == B * N * 3 * H * D
     o = torch.empty((B * N, H * D), device=qkv.device, dtype=BF16)
-    lse = torch.empty((B, H, N), device=qkv.device, dtype=F32) if want_lse else None
-    L.check(L.lib().cara_attn_fwd(qkv.data_ptr(), o.data_ptr(), _p(lse), B, N, H, D, scale, st), "cara_attn_fwd")
-    return o, lse
+    o_lo = torch.empty_like(o) if train else None
+    lse = torch.empty((B, H, N), device=qkv.device, dtype=F32) if train else None
+    L.check(L.lib().cara_attn_fwd(qkv.data_ptr(), o.data_ptr(), _p(o_lo), _p(lse), B, N, H, D, scale, st),
+            "cara_attn_fwd")
+    return o, o_lo, lse
 
 
-def attn_bwd(qkv, o, lse, d_o, B, N, H, D, scale):
+def attn_bwd(qkv, o, o_lo, lse, d_o, B, N, H, D, scale):
     st = _prep(qkv)
     assert d_o.is_contiguous() and d_o.dtype == BF16
     dqkv = torch.empty_like(qkv)
-    L.check(L.lib().cara_attn_bwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(), dqkv.data_ptr(),
-                                  B, N, H, D, scale, st), "cara_attn_bwd")
+    L.check(L.lib().cara_attn_bwd(qkv.data_ptr(), o.data_ptr(), o_lo.data_ptr(), lse.data_ptr(), d_o.data_ptr(),
+                                  dqkv.data_ptr(), B, N, H, D, scale, st), "cara_attn_bwd")
     return dqkv
 
 

@@ -78,13 +78,21 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None):
     if ops is None:
         dx = K.gemm_cp(G, fz.wt, epi=epi, aux=dgelu_aux) if need_dx else None
         return dx, None, None, None, None
-    R = ops.rank
-    dT, dcs = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T)
+    R, Rp, S = ops.rank, ops.rp, ops.slices
+    Kin, N = x.shape[1], G.shape[1]
+    w = N // S
+    # one zero fill for every atomically accumulated output of this projection's backward
+    sizes = (S * Rp, Kin * Rp, w * Rp, N if need_bias else 0)
+    z = torch.zeros(sum(sizes), device=G.device, dtype=F32)
+    zs = torch.split(z, sizes)
+    dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
+    colsum = zs[3] if need_bias else None
+    dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
     dx = None
     if need_dx:
         dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux)
-    dA, _ = K.adapter_cols(x, dT, 1, ops.rp)
-    dB, colsum = K.adapter_cols(G, U, ops.slices, ops.rp, want_colsum=need_bias)
+    K.adapter_cols(x, dT, 1, Rp, out=dA)
+    K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
     return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum
 
 
@@ -135,16 +143,16 @@ class AttnCoreFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qkv, B, N, H, D, scale):
-        o, lse = K.attn_fwd(qkv, B, N, H, D, scale, want_lse=True)
+        o, o_lo, lse = K.attn_fwd(qkv, B, N, H, D, scale, train=ctx.needs_input_grad[0])
         ctx.dims = (B, N, H, D, scale)
-        ctx.save_for_backward(qkv, o, lse)
+        ctx.save_for_backward(qkv, o, o_lo, lse)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
-        qkv, o, lse = ctx.saved_tensors
+        qkv, o, o_lo, lse = ctx.saved_tensors
         B, N, H, D, scale = ctx.dims
-        return K.attn_bwd(qkv, o, lse, d_o.contiguous(), B, N, H, D, scale), None, None, None, None, None
+        return K.attn_bwd(qkv, o, o_lo, lse, d_o.contiguous(), B, N, H, D, scale), None, None, None, None, None
 
 
 class LayerNormFunction(torch.autograd.Function):

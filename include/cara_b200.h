@@ -37,7 +37,7 @@ CARA_API int cara_set_device(int device);
  * bf16 operands, fp32 accumulation in tensor memory, bf16 outputs.
  *   epi = CARA_EPI_GELU : out (may be NULL) = pre-activation, out2 = GELU(pre-activation)
  *   epi = CARA_EPI_DGELU: out = (.) * gelu'(aux[M,N])   (dX through the fc1 activation)
- * Requirements: K0 % 8 == 0, N % 32 == 0, K1 % 16 == 0, 16-byte aligned bases and row pitches. */
+ * Requirements: K0 % 8 == 0, N % 64 == 0, K1 % 16 == 0, 16-byte aligned bases and row pitches. */
 typedef struct cara_gemm_desc {
   int M, N, K0;
   const void* A0; long lda0;
@@ -90,12 +90,14 @@ CARA_API int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int sl
 CARA_API int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, long ldv, int slices, int Rp,
                                float* out, float* colsum, void* stream);
 
-/* Attention core (cara.py:44-48) on the fused projection's [B,N,3,H,D] bf16 output; o is [B,N,H,D];
- * lse [B,H,N] fp32 (base-2 log-sum-exp of the scaled scores) is saved for backward.  D in {64,80}. */
-CARA_API int cara_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int D, float scale,
-                           void* stream);
-CARA_API int cara_attn_bwd(const void* qkv, const void* o, const float* lse, const void* d_o, void* dqkv, int B,
-                           int N, int H, int D, float scale, void* stream);
+/* Attention core (cara.py:44-48) on the fused projection's [B,N,3,H,D] bf16 output; o is [B,N,H,D].
+ * For training also pass lse [B,H,N] fp32 (base-2 log-sum-exp of the scaled scores) and o_lo [B,N,H,D] bf16
+ * (the rounding residual of o: o_fp32 = o + o_lo), both consumed by cara_attn_bwd; NULL for inference.
+ * D in {64,80}. */
+CARA_API int cara_attn_fwd(const void* qkv, void* o, void* o_lo, float* lse, int B, int N, int H, int D,
+                           float scale, void* stream);
+CARA_API int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float* lse, const void* d_o,
+                           void* dqkv, int B, int N, int H, int D, float scale, void* stream);
 
 /* timm PatchEmbed (conv PxP stride P) as im2col: img fp32 [B,Cin,S,S] -> bf16 [B*(S/P)^2, Kp] (zero padded),
  * then cara_gemm_cp against the flattened conv weight, then token assembly with cls/pos into the fp32

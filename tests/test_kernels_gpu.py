@@ -196,22 +196,26 @@ def test_gemm_adapter_segment_split_precision(K):
     assert abs(float((y - ref).mean())) < 1e-4 * float(ref.abs().mean()) + 1e-6
 
 
-@pytest.mark.parametrize("B,N,H,D", [(3, 197, 12, 64), (2, 257, 16, 80), (2, 64, 4, 64), (1, 50, 2, 64)])
+@pytest.mark.parametrize("B,N,H,D", [(3, 197, 12, 64), (2, 257, 16, 80), (2, 64, 4, 64), (1, 50, 2, 64), (2, 17, 3, 64),
+                                     (1, 128, 2, 80)])
 def test_attention_fwd_bwd(K, B, N, H, D):
     g = torch.Generator(device="cuda").manual_seed(6)
     C = H * D
     qkv = (torch.randn(B, N, 3, H, D, device="cuda", generator=g) * 1.0).to(BF16)
     scale = D ** -0.5
-    o, lse = K.attn_fwd(qkv.view(-1), B, N, H, D, scale)
+    o, o_lo, lse = K.attn_fwd(qkv.view(-1), B, N, H, D, scale)
     q, k, v = [t.float().requires_grad_(True) for t in qkv.permute(2, 0, 3, 1, 4)]
     att = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
     oref = (att @ v).transpose(1, 2).reshape(B * N, C)
     assert rel(o.float(), oref.detach()) < 6e-3
+    assert rel(o.float() + o_lo.float(), oref.detach()) < 3e-3      # (hi, lo) pair: only P's bf16 rounding is left
+    o_inf, no_lo, no_lse = K.attn_fwd(qkv.view(-1), B, N, H, D, scale, train=False)
+    assert no_lo is None and no_lse is None and torch.equal(o_inf, o)
     lref = torch.logsumexp((q @ k.transpose(-2, -1)) * scale, -1) / math.log(2.0)
     assert rel(lse, lref.detach()) < 1e-4
     d_o = torch.randn(B * N, C, device="cuda", generator=g).to(BF16)
     oref.backward(d_o.float())
-    dqkv = K.attn_bwd(qkv.view(-1), o, lse, d_o, B, N, H, D, scale).view(B, N, 3, H, D)
+    dqkv = K.attn_bwd(qkv.view(-1), o, o_lo, lse, d_o, B, N, H, D, scale).view(B, N, 3, H, D)
     dref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4)
     for i, name in enumerate("qkv"):
         assert rel(dqkv[:, :, i].float(), dref[:, :, i]) < 1.2e-2, name
