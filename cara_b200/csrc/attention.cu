@@ -83,16 +83,14 @@ __device__ __forceinline__ void load_a_frags(const HeadTile<D>& t, int row0, int
   for (int kk = 0; kk < D / 16; ++kk) ldsm_x4(t.at(row0 + (lane & 15), kk * 2 + (lane >> 4)), f[kk]);
 }
 
-// acc[j] (16 x 8 tiles, j over NT column tiles starting at row col0 of `t`) += A(16 x D) * t[col rows]^T;
-// only the first `ntp` 16-column pairs are computed (N is padded to 16, not to the chunk size)
+// acc[j] (16 x 8 tiles, j over NT column tiles starting at row col0 of `t`) += A(16 x D) * t[col rows]^T
 template <int D, int NT>
 __device__ __forceinline__ void mma_a_bt(const uint32_t (&af)[D / 16][4], const HeadTile<D>& t, int col0, int lane,
-                                         float (&acc)[NT][4], int ntp) {
+                                         float (&acc)[NT][4]) {
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
 #pragma unroll
     for (int jp = 0; jp < NT / 2; ++jp) {
-      if (jp >= ntp) continue;                      // warp-uniform: 16-column pairs past the padded length
       uint32_t bf[4];
       const int n = col0 + jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
       ldsm_x4(t.at(n, kk * 2 + ((lane >> 3) & 1)), bf);
@@ -105,11 +103,10 @@ __device__ __forceinline__ void mma_a_bt(const uint32_t (&af)[D / 16][4], const 
 // out[j] (16 x 8 tiles over D) += P(16 x 8*NT, fp32 accumulator layout, converted to bf16) * t[rows k0..]
 template <int D, int NT>
 __device__ __forceinline__ void mma_p_b(const float (&p)[NT][4], const HeadTile<D>& t, int k0, int lane,
-                                        float (&out)[D / 8][4], int ntp) {
+                                        float (&out)[D / 8][4]) {
   const int q = lane >> 3;
 #pragma unroll
   for (int ks = 0; ks < NT / 2; ++ks) {
-    if (ks >= ntp) continue;
     uint32_t af[4];
     af[0] = pack2(p[2 * ks][0], p[2 * ks][1]);
     af[1] = pack2(p[2 * ks][2], p[2 * ks][3]);
@@ -127,6 +124,103 @@ __device__ __forceinline__ void mma_p_b(const float (&p)[NT][4], const HeadTile<
 
 constexpr int KC = 64;   // keys per chunk (forward and dQ pass)
 constexpr int QC = 32;   // queries per chunk (dK/dV pass)
+
+// one chunk of NTP*16 keys of the forward: S = Q K^T, online softmax update, O += P V
+template <int D, int NTP>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&qf)[D / 16][4], const HeadTile<D>& tk, const HeadTile<D>& tv,
+                                          int k0, int N, int lane, float sl2, float& m_lo, float& m_hi, float& l_lo,
+                                          float& l_hi, float (&o)[D / 8][4]) {
+  constexpr int NT = NTP * 2;
+  const int t = lane & 3;
+  float s[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+  mma_a_bt<D, NT>(qf, tk, k0, lane, s);
+  float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int key = k0 + j * 8 + 2 * t;
+    s[j][0] = key < N ? s[j][0] * sl2 : -CUDART_INF_F;
+    s[j][1] = key + 1 < N ? s[j][1] * sl2 : -CUDART_INF_F;
+    s[j][2] = key < N ? s[j][2] * sl2 : -CUDART_INF_F;
+    s[j][3] = key + 1 < N ? s[j][3] * sl2 : -CUDART_INF_F;
+    mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
+  }
+  mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);      // finite: chunk 0 always holds key 0
+  const float c_lo = exp2f(m_lo - mx_lo), c_hi = exp2f(m_hi - mx_hi);
+  m_lo = mx_lo; m_hi = mx_hi;
+  l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) { o[j][0] *= c_lo; o[j][1] *= c_lo; o[j][2] *= c_hi; o[j][3] *= c_hi; }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    s[j][0] = exp2f(s[j][0] - m_lo); s[j][1] = exp2f(s[j][1] - m_lo);
+    s[j][2] = exp2f(s[j][2] - m_hi); s[j][3] = exp2f(s[j][3] - m_hi);
+    l_lo += s[j][0] + s[j][1]; l_hi += s[j][2] + s[j][3];
+  }
+  mma_p_b<D, NT>(s, tv, k0, lane, o);
+}
+
+// one chunk of NTP*16 keys of the dQ pass: recompute P, dP; dS = P (.) (dP - delta); dQ += dS K
+template <int D, int NTP>
+__device__ __forceinline__ void dq_chunk(const uint32_t (&qf)[D / 16][4], const uint32_t (&dof)[D / 16][4],
+                                         const HeadTile<D>& tk, const HeadTile<D>& tv, int k0, int N, int lane,
+                                         float sl2, float lse_lo, float lse_hi, float dl_lo, float dl_hi,
+                                         float (&dq)[D / 8][4]) {
+  constexpr int NT = NTP * 2;
+  const int t = lane & 3;
+  float s[NT][4], dp[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+  }
+  mma_a_bt<D, NT>(qf, tk, k0, lane, s);
+  mma_a_bt<D, NT>(dof, tv, k0, lane, dp);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int key = k0 + j * 8 + 2 * t;
+    const float p0 = key < N ? exp2f(s[j][0] * sl2 - lse_lo) : 0.f;
+    const float p1 = key + 1 < N ? exp2f(s[j][1] * sl2 - lse_lo) : 0.f;
+    const float p2 = key < N ? exp2f(s[j][2] * sl2 - lse_hi) : 0.f;
+    const float p3 = key + 1 < N ? exp2f(s[j][3] * sl2 - lse_hi) : 0.f;
+    s[j][0] = p0 * (dp[j][0] - dl_lo); s[j][1] = p1 * (dp[j][1] - dl_lo);
+    s[j][2] = p2 * (dp[j][2] - dl_hi); s[j][3] = p3 * (dp[j][3] - dl_hi);
+  }
+  mma_p_b<D, NT>(s, tk, k0, lane, dq);
+}
+
+// one chunk of NTP*16 queries of the dK/dV pass (transposed tiles: rows = keys, columns = queries)
+template <int D, int NTP>
+__device__ __forceinline__ void dkdv_chunk(const uint32_t (&kf)[D / 16][4], const uint32_t (&vf)[D / 16][4],
+                                           const HeadTile<D>& tq, const HeadTile<D>& tdo, int q0, int lane, float sl2,
+                                           const float* s_lse, const float* s_delta, float (&dk)[D / 8][4],
+                                           float (&dv)[D / 8][4]) {
+  constexpr int NT = NTP * 2;
+  const int t = lane & 3;
+  float st[NT][4], dpt[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+    dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
+  }
+  mma_a_bt<D, NT>(kf, tq, q0, lane, st);      // S^T = K Q^T
+  mma_a_bt<D, NT>(vf, tdo, q0, lane, dpt);    // dP^T = V dO^T
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int qi = q0 + j * 8 + 2 * t;
+    const float l0 = s_lse[qi], l1 = s_lse[qi + 1], d0 = s_delta[qi], d1 = s_delta[qi + 1];
+    const float p0 = exp2f(st[j][0] * sl2 - l0), p1 = exp2f(st[j][1] * sl2 - l1);
+    const float p2 = exp2f(st[j][2] * sl2 - l0), p3 = exp2f(st[j][3] * sl2 - l1);
+    dpt[j][0] = p0 * (dpt[j][0] - d0); dpt[j][1] = p1 * (dpt[j][1] - d1);
+    dpt[j][2] = p2 * (dpt[j][2] - d0); dpt[j][3] = p3 * (dpt[j][3] - d1);
+    st[j][0] = p0; st[j][1] = p1; st[j][2] = p2; st[j][3] = p3;
+  }
+  mma_p_b<D, NT>(st, tdo, q0, lane, dv);      // dV += P^T dO
+  mma_p_b<D, NT>(dpt, tq, q0, lane, dk);      // dK += dS^T Q
+}
+
 
 // ------------------------------------------------------------------------------------ forward
 template <int D>
@@ -154,36 +248,13 @@ attn_fwd_kernel(const AttnArgs a) {
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
     float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F, l_lo = 0.f, l_hi = 0.f;
-    for (int k0 = 0; k0 < npad; k0 += KC) {
-      float s[KC / 8][4];
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      const int ntp = min(KC / 16, (npad - k0) / 16);
-      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s, ntp);
-      float mx_lo = m_lo, mx_hi = m_hi;
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        const int key = k0 + j * 8 + 2 * t;
-        s[j][0] = key < N ? s[j][0] * sl2 : -CUDART_INF_F;
-        s[j][1] = key + 1 < N ? s[j][1] * sl2 : -CUDART_INF_F;
-        s[j][2] = key < N ? s[j][2] * sl2 : -CUDART_INF_F;
-        s[j][3] = key + 1 < N ? s[j][3] * sl2 : -CUDART_INF_F;
-        mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
-        mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
-      }
-      mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);      // finite: chunk 0 always holds key 0
-      const float c_lo = exp2f(m_lo - mx_lo), c_hi = exp2f(m_hi - mx_hi);
-      m_lo = mx_lo; m_hi = mx_hi;
-      l_lo *= c_lo; l_hi *= c_hi;
-#pragma unroll
-      for (int j = 0; j < D / 8; ++j) { o[j][0] *= c_lo; o[j][1] *= c_lo; o[j][2] *= c_hi; o[j][3] *= c_hi; }
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        s[j][0] = exp2f(s[j][0] - m_lo); s[j][1] = exp2f(s[j][1] - m_lo);
-        s[j][2] = exp2f(s[j][2] - m_hi); s[j][3] = exp2f(s[j][3] - m_hi);
-        l_lo += s[j][0] + s[j][1]; l_hi += s[j][2] + s[j][3];
-      }
-      mma_p_b<D, KC / 8>(s, tv, k0, lane, o, ntp);
+    int k0 = 0;
+    for (; k0 + KC <= npad; k0 += KC) fwd_chunk<D, KC / 16>(qf, tk, tv, k0, N, lane, sl2, m_lo, m_hi, l_lo, l_hi, o);
+    switch ((npad - k0) / 16) {                    // N is padded to 16 keys, not to the chunk size
+      case 1: fwd_chunk<D, 1>(qf, tk, tv, k0, N, lane, sl2, m_lo, m_hi, l_lo, l_hi, o); break;
+      case 2: fwd_chunk<D, 2>(qf, tk, tv, k0, N, lane, sl2, m_lo, m_hi, l_lo, l_hi, o); break;
+      case 3: fwd_chunk<D, 3>(qf, tk, tv, k0, N, lane, sl2, m_lo, m_hi, l_lo, l_hi, o); break;
+      default: break;
     }
     l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
     const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
@@ -276,27 +347,14 @@ attn_bwd_kernel(const AttnArgs a) {
     float dq[D / 8][4];
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
-    for (int k0 = 0; k0 < npad; k0 += KC) {
-      float s[KC / 8][4], dp[KC / 8][4];
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-      }
-      const int ntp = min(KC / 16, (npad - k0) / 16);
-      mma_a_bt<D, KC / 8>(qf, tk, k0, lane, s, ntp);
-      mma_a_bt<D, KC / 8>(dof, tv, k0, lane, dp, ntp);
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        const int key = k0 + j * 8 + 2 * t;
-        const float p0 = key < N ? exp2f(s[j][0] * sl2 - lse_lo) : 0.f;
-        const float p1 = key + 1 < N ? exp2f(s[j][1] * sl2 - lse_lo) : 0.f;
-        const float p2 = key < N ? exp2f(s[j][2] * sl2 - lse_hi) : 0.f;
-        const float p3 = key + 1 < N ? exp2f(s[j][3] * sl2 - lse_hi) : 0.f;
-        s[j][0] = p0 * (dp[j][0] - dl_lo); s[j][1] = p1 * (dp[j][1] - dl_lo);
-        s[j][2] = p2 * (dp[j][2] - dl_hi); s[j][3] = p3 * (dp[j][3] - dl_hi);
-      }
-      mma_p_b<D, KC / 8>(s, tk, k0, lane, dq, ntp);
+    int k0 = 0;
+    for (; k0 + KC <= npad; k0 += KC)
+      dq_chunk<D, KC / 16>(qf, dof, tk, tv, k0, N, lane, sl2, lse_lo, lse_hi, dl_lo, dl_hi, dq);
+    switch ((npad - k0) / 16) {
+      case 1: dq_chunk<D, 1>(qf, dof, tk, tv, k0, N, lane, sl2, lse_lo, lse_hi, dl_lo, dl_hi, dq); break;
+      case 2: dq_chunk<D, 2>(qf, dof, tk, tv, k0, N, lane, sl2, lse_lo, lse_hi, dl_lo, dl_hi, dq); break;
+      case 3: dq_chunk<D, 3>(qf, dof, tk, tv, k0, N, lane, sl2, lse_lo, lse_hi, dl_lo, dl_hi, dq); break;
+      default: break;
     }
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) {
@@ -317,29 +375,9 @@ attn_bwd_kernel(const AttnArgs a) {
       dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
       dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
     }
-    for (int q0 = 0; q0 < npad; q0 += QC) {
-      float st[QC / 8][4], dpt[QC / 8][4];
-#pragma unroll
-      for (int j = 0; j < QC / 8; ++j) {
-        st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
-        dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
-      }
-      const int ntp = min(QC / 16, (npad - q0) / 16);
-      mma_a_bt<D, QC / 8>(kf, tq, q0, lane, st, ntp);     // S^T = K Q^T
-      mma_a_bt<D, QC / 8>(vf, tdo, q0, lane, dpt, ntp);   // dP^T = V dO^T
-#pragma unroll
-      for (int j = 0; j < QC / 8; ++j) {
-        const int qi = q0 + j * 8 + 2 * t;
-        const float l0 = s_lse[qi], l1 = s_lse[qi + 1], d0 = s_delta[qi], d1 = s_delta[qi + 1];
-        const float p0 = exp2f(st[j][0] * sl2 - l0), p1 = exp2f(st[j][1] * sl2 - l1);
-        const float p2 = exp2f(st[j][2] * sl2 - l0), p3 = exp2f(st[j][3] * sl2 - l1);
-        dpt[j][0] = p0 * (dpt[j][0] - d0); dpt[j][1] = p1 * (dpt[j][1] - d1);
-        dpt[j][2] = p2 * (dpt[j][2] - d0); dpt[j][3] = p3 * (dpt[j][3] - d1);
-        st[j][0] = p0; st[j][1] = p1; st[j][2] = p2; st[j][3] = p3;
-      }
-      mma_p_b<D, QC / 8>(st, tdo, q0, lane, dv, ntp);     // dV += P^T dO
-      mma_p_b<D, QC / 8>(dpt, tq, q0, lane, dk, ntp);     // dK += dS^T Q
-    }
+    int q0 = 0;
+    for (; q0 + QC <= npad; q0 += QC) dkdv_chunk<D, QC / 16>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv);
+    if (q0 < npad) dkdv_chunk<D, 1>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv);
     const int r_lo = kt * 16 + g, r_hi = r_lo + 8;
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) {
