@@ -55,13 +55,17 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// Shared-memory tile of one head: rows of D bf16 padded by 16 B so the eight 16-byte rows an ldmatrix
-// phase touches fall in distinct bank groups (pitch mod 128 = 16 for D = 64, 48 for D = 80).
+// Shared-memory tile of one head, conflict-free for ldmatrix (eight 16-byte rows per phase must fall in distinct
+// bank groups): D = 64 -> dense 128-byte rows with the 16-byte chunk index XOR-swizzled by (row & 7), so four
+// tiles of 208 rows fit twice per SM; other D -> rows padded by 16 B (pitch mod 128 = 48 for D = 80).
 template <int D>
 struct HeadTile {
-  static constexpr int PITCH = D * 2 + 16;
+  static constexpr int PITCH = D == 64 ? 128 : D * 2 + 16;
   uint32_t base;
-  __device__ __forceinline__ uint32_t at(int row, int chunk16) const { return base + row * PITCH + chunk16 * 16; }
+  __device__ __forceinline__ uint32_t at(int row, int chunk16) const {
+    if (D == 64) return base + row * 128 + ((chunk16 ^ (row & 7)) << 4);
+    return base + row * PITCH + chunk16 * 16;
+  }
 };
 
 // cooperative load of rows [0, npad) of one of q/k/v (or dO) for head (b,h); rows >= N are zero-filled
@@ -123,7 +127,7 @@ __device__ __forceinline__ void mma_p_b(const float (&p)[NT][4], const HeadTile<
 }
 
 constexpr int KC = 64;   // keys per chunk (forward and dQ pass)
-constexpr int QC = 32;   // queries per chunk (dK/dV pass)
+constexpr int QC = 64;   // queries per chunk (dK/dV pass)
 
 // one chunk of NTP*16 keys of the forward: S = Q K^T, online softmax update, O += P V
 template <int D, int NTP>
@@ -223,8 +227,10 @@ __device__ __forceinline__ void dkdv_chunk(const uint32_t (&kf)[D / 16][4], cons
 
 
 // ------------------------------------------------------------------------------------ forward
+constexpr int FWD_THREADS = 256;
+
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FWD_THREADS, D == 64 ? 2 : 1)
 attn_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -233,15 +239,15 @@ attn_fwd_kernel(const AttnArgs a) {
   const long pitch = 3L * a.H * D;
   const __nv_bfloat16* base = a.qkv + static_cast<long>(b) * N * pitch + h * D;
   HeadTile<D> tq{s_u32(smem)}, tk{tq.base + npad * HeadTile<D>::PITCH}, tv{tk.base + npad * HeadTile<D>::PITCH};
-  load_head<D>(tq, base, pitch, N, npad, tid, 128);
-  load_head<D>(tk, base + a.H * D, pitch, N, npad, tid, 128);
-  load_head<D>(tv, base + 2 * a.H * D, pitch, N, npad, tid, 128);
+  load_head<D>(tq, base, pitch, N, npad, tid, FWD_THREADS);
+  load_head<D>(tk, base + a.H * D, pitch, N, npad, tid, FWD_THREADS);
+  load_head<D>(tv, base + 2 * a.H * D, pitch, N, npad, tid, FWD_THREADS);
   cp_async_commit_wait_all();
   __syncthreads();
 
   const float sl2 = a.scale * 1.4426950408889634f;
   const int g = lane >> 2, t = lane & 3;
-  for (int qt = warp; qt * 16 < N; qt += 4) {
+  for (int qt = warp; qt * 16 < N; qt += FWD_THREADS / 32) {
     uint32_t qf[D / 16][4];
     load_a_frags<D>(tq, qt * 16, lane, qf);
     float o[D / 8][4];
@@ -285,14 +291,16 @@ attn_fwd_kernel(const AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------ backward
+constexpr int BWD_THREADS = 128;
+
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BWD_THREADS, D == 64 ? 2 : 1)
 attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int NW = 8;
+  constexpr int NW = BWD_THREADS / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int N = a.N, npad = ((N + 15) / 16) * 16, nstat = ((N + 31) / 32) * 32;
+  const int N = a.N, npad = ((N + 15) / 16) * 16, nstat = ((N + QC - 1) / QC) * QC;
   const int C = a.H * D;
   const long pitch = 3L * C;
   const __nv_bfloat16* base = a.qkv + static_cast<long>(b) * N * pitch + h * D;
@@ -303,30 +311,46 @@ attn_bwd_kernel(const AttnArgs a) {
   HeadTile<D> tq{s_u32(smem)}, tk{tq.base + npad * TB}, tv{tk.base + npad * TB}, tdo{tv.base + npad * TB};
   float* s_lse = reinterpret_cast<float*>(smem + 4 * npad * TB);
   float* s_delta = s_lse + nstat;
-  load_head<D>(tq, base, pitch, N, npad, tid, 256);
-  load_head<D>(tk, base + C, pitch, N, npad, tid, 256);
-  load_head<D>(tv, base + 2 * C, pitch, N, npad, tid, 256);
-  load_head<D>(tdo, dob, C, N, npad, tid, 256);
+  load_head<D>(tq, base, pitch, N, npad, tid, BWD_THREADS);
+  load_head<D>(tk, base + C, pitch, N, npad, tid, BWD_THREADS);
+  load_head<D>(tv, base + 2 * C, pitch, N, npad, tid, BWD_THREADS);
+  load_head<D>(tdo, dob, C, N, npad, tid, BWD_THREADS);
   // delta_i = sum_d dO[i,d] (O + O_lo)[i,d]: O carried as a bf16 (hi, lo) pair, because with the plain bf16 O
   // the rounding of O is the dominant dq/dk error for peaked softmax rows (rows of dS no longer sum to ~0).
   // lse padded with +big so padded queries get P = 0 in pass 2.
   const float* lse = a.lse + (static_cast<long>(b) * a.H + h) * N;
-  for (int row = warp; row < nstat; row += NW) {
-    float acc = 0.f;
-    if (row < N) {
-      for (int d = lane * 2; d < D; d += 64) {
-        const long off = static_cast<long>(row) * C + d;
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + off));
-        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + off));
-        const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(olb + off));
-        acc += x.x * (y.x + z.x) + x.y * (y.y + z.y);
-      }
-    }
+  for (int row = tid; row < nstat; row += BWD_THREADS) {
+    s_lse[row] = row < N ? lse[row] : 1e30f;
+    s_delta[row] = 0.f;
+  }
+  __syncthreads();
+  {
+    // all threads, 16-byte coalesced loads, two items in flight per thread: the global-latency part of the CTA
+    constexpr int CH = D / 8;
+    auto dot8 = [](const uint4& x, const uint4& y, const uint4& z) {
+      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w}, zw[4] = {z.x, z.y, z.z, z.w};
+      float acc = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      s_delta[row] = acc;
-      s_lse[row] = row < N ? lse[row] : 1e30f;
+      for (int e = 0; e < 4; ++e) {
+        const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[e]));
+        const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[e]));
+        const float2 zf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zw[e]));
+        acc += xf.x * (yf.x + zf.x) + xf.y * (yf.y + zf.y);
+      }
+      return acc;
+    };
+    const int items = N * CH;
+    for (int i0 = tid; i0 < items; i0 += 2 * BWD_THREADS) {
+      const int i1 = i0 + BWD_THREADS;
+      const bool has1 = i1 < items;
+      const int r0 = i0 / CH, c0 = i0 % CH, r1 = has1 ? i1 / CH : r0, c1 = has1 ? i1 % CH : c0;
+      const long o0 = static_cast<long>(r0) * C + c0 * 8, o1 = static_cast<long>(r1) * C + c1 * 8;
+      const uint4 x0 = *reinterpret_cast<const uint4*>(dob + o0), y0 = *reinterpret_cast<const uint4*>(ob + o0),
+                  z0 = *reinterpret_cast<const uint4*>(olb + o0);
+      const uint4 x1 = *reinterpret_cast<const uint4*>(dob + o1), y1 = *reinterpret_cast<const uint4*>(ob + o1),
+                  z1 = *reinterpret_cast<const uint4*>(olb + o1);
+      atomicAdd(&s_delta[r0], dot8(x0, y0, z0));
+      if (has1) atomicAdd(&s_delta[r1], dot8(x1, y1, z1));
     }
   }
   cp_async_commit_wait_all();
@@ -377,7 +401,12 @@ attn_bwd_kernel(const AttnArgs a) {
     }
     int q0 = 0;
     for (; q0 + QC <= npad; q0 += QC) dkdv_chunk<D, QC / 16>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv);
-    if (q0 < npad) dkdv_chunk<D, 1>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv);
+    switch ((npad - q0) / 16) {
+      case 1: dkdv_chunk<D, 1>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv); break;
+      case 2: dkdv_chunk<D, 2>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv); break;
+      case 3: dkdv_chunk<D, 3>(kf, vf, tq, tdo, q0, lane, sl2, s_lse, s_delta, dk, dv); break;
+      default: break;
+    }
     const int r_lo = kt * 16 + g, r_hi = r_lo + 8;
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) {
@@ -404,12 +433,12 @@ int fwd_t(const AttnArgs& a, cudaStream_t st) {
     if (cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -52;
     configured = smem;
   }
-  attn_fwd_kernel<D><<<a.B * a.H, 128, smem, st>>>(a);
+  attn_fwd_kernel<D><<<a.B * a.H, FWD_THREADS, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -53;
 }
 template <int D>
 int bwd_t(const AttnArgs& a, cudaStream_t st) {
-  const int npad = ((a.N + 15) / 16) * 16, nstat = ((a.N + 31) / 32) * 32;
+  const int npad = ((a.N + 15) / 16) * 16, nstat = ((a.N + QC - 1) / QC) * QC;
   const int smem = 4 * npad * HeadTile<D>::PITCH + 2 * nstat * 4;
   if (smem > 227 * 1024) return -51;
   static int configured = 0;
@@ -417,7 +446,7 @@ int bwd_t(const AttnArgs& a, cudaStream_t st) {
     if (cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -52;
     configured = smem;
   }
-  attn_bwd_kernel<D><<<a.B * a.H, 256, smem, st>>>(a);
+  attn_bwd_kernel<D><<<a.B * a.H, BWD_THREADS, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -53;
 }
 
