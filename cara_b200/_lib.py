@@ -24,7 +24,7 @@ class GemmDesc(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int),
         ("out2", C.c_void_p), ("ldo2", C.c_int),
         ("aux", C.c_void_p), ("ldaux", C.c_int),
-        ("epi", C.c_int), ("num_sms", C.c_int),
+        ("epi", C.c_int), ("num_sms", C.c_int), ("pair", C.c_int),
     ]
 
 

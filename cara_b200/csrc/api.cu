@@ -43,7 +43,7 @@ int cara_gemm_cp(const cara_gemm_desc* d, void* stream) {
   g.out = static_cast<__nv_bfloat16*>(d->out); g.ldo = d->ldo;
   g.out2 = static_cast<__nv_bfloat16*>(d->out2); g.ldo2 = d->ldo2;
   g.aux = static_cast<const __nv_bfloat16*>(d->aux); g.ldaux = d->ldaux;
-  g.epi = d->epi; g.num_sms = d->num_sms;
+  g.epi = d->epi; g.num_sms = d->num_sms; g.pair = d->pair;
   int rc = cara::gemm_cp_launch(g, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(rc, "cara_gemm_cp: launch failed / bad arguments");
   return 0;

@@ -9,12 +9,14 @@
 // the frozen product -- the delta weight of cara.py:27-35,52-57,76-81,88-92 is never materialised and
 // no second [M,N] pass exists.
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer + TMEM
-// owner, warps 2..5 = epilogue.  Two 256-column fp32 accumulators in TMEM let the epilogue of tile i
-// overlap the main loop of tile i+1.  Epilogue data path: tcgen05.ld -> registers (bias / GELU / GELU')
-// -> 128-byte-swizzled shared staging (conflict-free 16-byte stores) -> TMA tensor store, 32 rows x 64
-// columns per warp and step, double buffered; the GELU' operand arrives the same way through TMA loads
-// prefetched one step ahead.  HBM therefore only ever sees full 128-byte lines.
+// Roles: warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer + TMEM owner, then the
+// epilogue warps: 4 for the plain epilogue, 8 (two per TMEM lane group, each taking half of the 256
+// columns) for the GELU / GELU' epilogues whose per-element math would otherwise outlast the K = 768 main
+// loop.  Two 256-column fp32 accumulators in TMEM let the epilogue of tile i overlap the main loop of tile
+// i+1.  Epilogue data path: tcgen05.ld -> registers (bias / GELU / GELU') -> 128-byte-swizzled shared
+// staging (conflict-free 16-byte accesses) -> TMA tensor store, 32 rows x 64 columns per warp and step;
+// the GELU' operand arrives the same way through TMA loads prefetched one step ahead and is overwritten in
+// place by the result.  HBM therefore only ever sees full 128-byte lines.
 #include "ptx.cuh"
 #include "gemm_sm100.h"
 #include "mathfn.cuh"
@@ -24,47 +26,63 @@ namespace cara {
 constexpr int BM = 128, BN = 256, BK = 64;      // CTA tile; BK*2B = one 128-byte swizzle row
 constexpr int UK = 16;                          // tcgen05 kind::f16 K per instruction
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-constexpr int B_BYTES = BN * BK * 2;            // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int TMEM_COLS = 512;                  // 2 accumulators x 256 fp32 columns
-constexpr int NUM_THREADS = 192;
+// PAIR = two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 on a 256 x 256 tile: each CTA stages its own
+// 128 rows of A and HALF of the B tile, so L2 -> SM traffic per flop drops by a third and the ring gets 6 stages
+// instead of 4.  (The single-CTA kernel measured ~13-15 TB/s of L2 -> SM operand traffic: the L2 bound.)
+__host__ __device__ constexpr int b_rows(bool pair) { return pair ? BN / 2 : BN; }
+__host__ __device__ constexpr int stage_bytes(bool pair) { return A_BYTES + b_rows(pair) * BK * 2; }
 constexpr int EC = 64;                          // epilogue step: 64 output columns = one 128-B swizzle row
-constexpr int EBUF = 32 * EC * 2;               // 4 KB staging buffer: 32 rows x 128 B
-// main-loop ring depth / staging tensors per epilogue kind (smem budget 227 KB)
-__host__ __device__ constexpr int num_stages(int epi) { return epi == EPI_NONE ? 4 : 3; }
-__host__ __device__ constexpr int num_stage_tensors(int epi) { return epi == EPI_NONE ? 1 : 2; }
-__host__ __device__ constexpr int gemm_smem(int epi) {
-  return num_stages(epi) * STAGE_BYTES + 4 * 2 * EBUF * num_stage_tensors(epi) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EBUF = 32 * EC * 2;               // 4 KB staging buffer: 32 rows x 128 B; two per epilogue warp
+// main-loop ring depth / epilogue warps per epilogue kind (smem budget 227 KB)
+// (measured: the GELU kinds are bound by main-loop ring depth, not by epilogue math -- 3 stages + 8 epilogue
+// warps ran at 288 us where 4 stages + 4 warps ... see profiles/)
+__host__ __device__ constexpr int num_stages(int epi, bool pair) { return pair ? 6 : 4; }
+__host__ __device__ constexpr int num_epi_warps(int epi) { return epi == EPI_DGELU ? 8 : 4; }
+__host__ __device__ constexpr int num_threads(int epi) { return 64 + 32 * num_epi_warps(epi); }
+__host__ __device__ constexpr int gemm_smem(int epi, bool pair) {
+  int stages = num_stages(epi, pair);
+  while (stages * stage_bytes(pair) + num_epi_warps(epi) * 2 * EBUF + 1024 + 512 > 227 * 1024) --stages;
+  return stages * stage_bytes(pair) + num_epi_warps(epi) * 2 * EBUF + 1024 /*align slack*/ + 512 /*barriers*/;
+}
+__host__ __device__ constexpr int fitted_stages(int epi, bool pair) {
+  int stages = num_stages(epi, pair);
+  while (stages * stage_bytes(pair) + num_epi_warps(epi) * 2 * EBUF + 1024 + 512 > 227 * 1024) --stages;
+  return stages;
 }
 
 struct TileCoord {
   int m0, n0;
 };
-__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_n) {
-  // n fastest: the CTAs resident at one time share a handful of A row-panels and all of B through L2
-  return {(t / tiles_n) * BM, (t % tiles_n) * BN};
-}
 
-template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int EPI, bool PAIR>
+__global__ void __launch_bounds__(num_threads(EPI), 1)
 gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAux,
                const GemmArgs p) {
-  constexpr int STAGES = num_stages(EPI);
-  constexpr int NST = num_stage_tensors(EPI);
+  constexpr int STAGES = fitted_stages(EPI, PAIR);
+  constexpr int EW = num_epi_warps(EPI);
+  constexpr int STAGE_BYTES = stage_bytes(PAIR);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader of the CTA pair
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nunits = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // n fastest: the CTAs resident at one time share a handful of A row-panels and all of B through L2
+  auto tile_coord = [&](int t) {
+    return TileCoord{(t / p.tiles_n) * (PAIR ? 2 * BM : BM) + static_cast<int>(rank) * BM, (t % p.tiles_n) * BN};
+  };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-B alignment
-  const uint32_t stage_out = tiles + STAGES * STAGE_BYTES; // [4 warps][NST tensors][2 buffers][4 KB]
-  const uint32_t bars = stage_out + 4 * 2 * EBUF * NST;
-  // barrier map (8 B each): full[S], empty[S], tfull[2], tempty[2], aux[4 warps][2], then the TMEM base word
+  const uint32_t stage_out = tiles + STAGES * STAGE_BYTES; // [EW warps][2 buffers][4 KB]
+  const uint32_t bars = stage_out + EW * 2 * EBUF;
+  // barrier map (8 B each): full[S], empty[S], tfull[2], tempty[2], aux[EW warps][2], then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   auto aux_bar = [&](int w, int b) { return bars + 8u * (2 * STAGES + 4 + w * 2 + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 12);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4 + 2 * EW);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -82,14 +100,14 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tma_prefetch_desc(&mapB1);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), PAIR ? 2 : 1);      // pair: leader's arrive.expect_tx + the peer producer's arrive
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), PAIR ? 2 * EW : EW);  // one arrive per epilogue warp (of both CTAs)
     }
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < EW; ++w) {
       mbar_init(aux_bar(w, 0), 1);
       mbar_init(aux_bar(w, 1), 1);
     }
@@ -97,9 +115,11 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (EPI != EPI_NONE) tma_prefetch_desc(&mapAux);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers + TMEM visible (to the peer CTA as well)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -108,35 +128,41 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(t, p.tiles_n);
+      const int b_off = PAIR ? static_cast<int>(rank) * (BN / 2) : 0;   // pair: this CTA stages half of the B rows
+      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+        if (PAIR) tma_load_2d_pair(dst, m, bar, c0, c1); else tma_load_2d(dst, m, bar, c0, c1);
+      };
+      for (int t = unit; t < num_tiles; t += nunits) {
+        const TileCoord tc = tile_coord(t);
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_wait(empty_bar(s), ph ^ 1u);       // own stage free (pair: the leader's commit is multicast to both)
           const uint32_t sa = tiles + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          if (!PAIR) mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          else if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
           if (kb < p.kblocks_main) {
-            tma_load_2d(sa, &mapA0, full_bar(s), kb * BK, tc.m0);
-            tma_load_2d(sb, &mapB0, full_bar(s), kb * BK, tc.n0);
+            load(sa, &mapA0, full_bar(s), kb * BK, tc.m0);
+            load(sb, &mapB0, full_bar(s), kb * BK, tc.n0 + b_off);
           } else {
             const int e = kb - p.kblocks_main;
             const int slice = tc.n0 / p.ext_slice_w;
-            tma_load_2d(sa, &mapA1, full_bar(s), slice * p.ext_rp + e * BK, tc.m0);
-            tma_load_2d(sb, &mapB1, full_bar(s), e * BK, tc.n0 - slice * p.ext_slice_w);
+            load(sa, &mapA1, full_bar(s), slice * p.ext_rp + e * BK, tc.m0);
+            load(sb, &mapB1, full_bar(s), e * BK, tc.n0 - slice * p.ext_slice_w + b_off);
           }
+          if (PAIR && rank != 0) mbar_arrive_remote(full_bar(s), 0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = unit; t < num_tiles; t += nunits) {
         mbar_wait(tempty_bar(as), aph ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -153,51 +179,63 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));              // frees the smem stage when these MMAs retire
-          if (kb == kblocks - 1) umma_commit(tfull_bar(as));
+          // when these MMAs retire: free the smem stage (in both CTAs of a pair) / publish the accumulator
+          if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
+          if (kb == kblocks - 1) {
+            if (PAIR) umma_commit_pair(tfull_bar(as)); else umma_commit(tfull_bar(as));
+          }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------------ epilogue warps
     const int lg = warp & 3;                      // TMEM lane group this warp may touch
     const int ew = warp - 2;                      // staging slot of this warp
-    const uint32_t my_stage = stage_out + ew * (2 * EBUF * NST);   // tensor 0: [2][EBUF]; tensor 1: [2][EBUF]
+    constexpr int NCH = (BN / EC) * 4 / EW;       // 64-column steps per warp and tile (4, or 2 with 8 warps)
+    const int c_first = (ew >> 2) * NCH;          // with 8 warps the second four take the upper 128 columns
+    const uint32_t my_stage = stage_out + ew * (2 * EBUF);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);          // 128-B swizzle phase of this thread's row
     const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
     int as = 0;
     uint32_t aph = 0;
-    uint32_t q = 0;                               // running 64-column step counter (buffer / parity selector)
-    if (EPI == EPI_DGELU && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) {
-      const TileCoord t0 = tile_coord(blockIdx.x, p.tiles_n);
+    uint32_t q = 0;                               // running step counter of this warp (buffer / parity selector)
+    if (EPI == EPI_DGELU && lane == 0 && unit < num_tiles) {
+      const TileCoord t0 = tile_coord(unit);
       mbar_expect_tx(aux_bar(ew, 0), EBUF);
-      tma_load_2d(my_stage + 2 * EBUF, &mapAux, aux_bar(ew, 0), t0.n0, t0.m0 + lg * 32);
+      tma_load_2d(my_stage, &mapAux, aux_bar(ew, 0), t0.n0 + c_first * EC, t0.m0 + lg * 32);
     }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const TileCoord tc = tile_coord(t, p.tiles_n);
+    for (int t = unit; t < num_tiles; t += nunits) {
+      const TileCoord tc = tile_coord(t);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / EC; ++c, ++q) {
+      for (int ci = 0; ci < NCH; ++ci, ++q) {
+        const int c = c_first + ci;
         const uint32_t b = q & 1u;
-        const uint32_t so = my_stage + b * EBUF;                  // staging of the primary output
-        const uint32_t sx = my_stage + 2 * EBUF + b * EBUF;       // second tensor: GELU output / GELU' operand
-        // the TMA store that read this buffer two steps ago must have drained it
-        if (lane == 0) tma_store_wait_read<1>();
+        // Staging use per kind.  NONE: out double-buffered in buf[b].  GELU: buf[0] = pre-activation,
+        // buf[1] = GELU output (single-buffered).  DGELU: buf[b] holds the TMA-loaded u tile and is
+        // overwritten in place by the result.
+        const uint32_t so = EPI == EPI_GELU ? my_stage : my_stage + b * EBUF;
+        const uint32_t sx = EPI == EPI_GELU ? my_stage + EBUF : so;
+        // earlier TMA stores must have finished READING the buffer(s) this step writes
+        if (lane == 0) {
+          if (EPI == EPI_NONE) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
         __syncwarp();
         if (EPI == EPI_DGELU) {
-          if (lane == 0) {                                        // prefetch the next step's operand tile
-            int nt = t, nc = c + 1;
-            if (nc == BN / EC) { nt = t + gridDim.x; nc = 0; }
+          if (lane == 0) {                                        // prefetch the next step's u tile
+            int nt = t, nci = ci + 1;
+            if (nci == NCH) { nt = t + nunits; nci = 0; }
             if (nt < num_tiles) {
-              const TileCoord tn = tile_coord(nt, p.tiles_n);
+              const TileCoord tn = tile_coord(nt);
               mbar_expect_tx(aux_bar(ew, b ^ 1u), EBUF);
-              tma_load_2d(my_stage + 2 * EBUF + (b ^ 1u) * EBUF, &mapAux, aux_bar(ew, b ^ 1u), tn.n0 + nc * EC,
+              tma_load_2d(my_stage + (b ^ 1u) * EBUF, &mapAux, aux_bar(ew, b ^ 1u), tn.n0 + (c_first + nci) * EC,
                           tn.m0 + lg * 32);
             }
           }
@@ -207,6 +245,13 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tmem_ld32(t_row + c * EC, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         tmem_ld32(t_row + c * EC + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
+        if (ci == NCH - 1) {                                      // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
+          }
+        }
         const int n = tc.n0 + c * EC;
         if (p.bias != nullptr && n < p.N) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
@@ -254,11 +299,6 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sx + off), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
           }
         }
-        if (c == BN / EC - 1) {                                   // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
-        }
         fence_proxy_async();                                      // staging writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
@@ -272,11 +312,12 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (lane == 0) tma_store_wait<0>();                           // all output bytes are in global memory
   }
 
+  __syncwarp();                                            // reconverge the single-lane role warps
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: the peer may still be reading / being signalled
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -314,18 +355,41 @@ static int make_map_bf16(CUtensorMap* map, const void* base, long rows, long col
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-template <int EPI>
+template <int EPI, bool PAIR>
 static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                               const CUtensorMap& b1, const CUtensorMap& mo, const CUtensorMap& mx,
                               const GemmArgs& args, int grid, cudaStream_t st) {
   static bool attr_done = false;
+  constexpr int smem = gemm_smem(EPI, PAIR);
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_cp_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(EPI));
+    cudaError_t e = cudaFuncSetAttribute(gemm_cp_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  gemm_cp_kernel<EPI><<<grid, NUM_THREADS, gemm_smem(EPI), st>>>(a0, b0, a1, b1, mo, mx, args);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(num_threads(EPI));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_cp_kernel<EPI, PAIR>, a0, b0, a1, b1, mo, mx, args);
+}
+
+template <bool PAIR>
+static cudaError_t launch_kind(int epi, const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
+                               const CUtensorMap& b1, const CUtensorMap& mo, const CUtensorMap& mx,
+                               const GemmArgs& args, int grid, cudaStream_t st) {
+  switch (epi) {
+    case EPI_NONE: return launch_epi<EPI_NONE, PAIR>(a0, b0, a1, b1, mo, mx, args, grid, st);
+    case EPI_GELU: return launch_epi<EPI_GELU, PAIR>(a0, b0, a1, b1, mo, mx, args, grid, st);
+    default: return launch_epi<EPI_DGELU, PAIR>(a0, b0, a1, b1, mo, mx, args, grid, st);
+  }
 }
 
 int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
@@ -333,8 +397,9 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   if (d.out == nullptr && d.epi != EPI_GELU) return -16;
   CUtensorMap a0, b0, a1, b1, mo, mx;
   int rc;
+  const bool pair = d.pair != 0;
   if ((rc = make_map_bf16(&a0, d.A0, d.M, d.K0, d.lda0, BM)) != 0) return rc * 10 - 1;
-  if ((rc = make_map_bf16(&b0, d.B0, d.N, d.K0, d.ldb0, BN)) != 0) return rc * 10 - 2;
+  if ((rc = make_map_bf16(&b0, d.B0, d.N, d.K0, d.ldb0, b_rows(pair))) != 0) return rc * 10 - 2;
   GemmArgs args{};
   args.M = d.M; args.N = d.N;
   args.kblocks_main = (d.K0 + BK - 1) / BK;
@@ -345,7 +410,7 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
     const int slice_w = d.N / d.ext_slices;
     if (d.ext_slices > 1 && (slice_w % BN) != 0) return -12;
     if ((rc = make_map_bf16(&a1, d.A1, d.M, static_cast<long>(d.K1) * d.ext_slices, d.lda1, BM)) != 0) return rc * 10 - 3;
-    if ((rc = make_map_bf16(&b1, d.B1, slice_w, d.K1, d.ldb1, BN)) != 0) return rc * 10 - 4;
+    if ((rc = make_map_bf16(&b1, d.B1, slice_w, d.K1, d.ldb1, b_rows(pair))) != 0) return rc * 10 - 4;
     args.ksteps_ext = d.K1 / UK;
     args.ext_slice_w = slice_w;
     args.ext_rp = d.K1;
@@ -356,11 +421,17 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   args.out = d.out; args.ldo = d.ldo;
   args.out2 = d.out2; args.ldo2 = d.ldo2;
   args.aux = d.aux; args.ldaux = d.ldaux;
-  args.tiles_m = (d.M + BM - 1) / BM;
+  const int tile_m = pair ? 2 * BM : BM;
+  args.tiles_m = (d.M + tile_m - 1) / tile_m;
   args.tiles_n = (d.N + BN - 1) / BN;
   const int num_tiles = args.tiles_m * args.tiles_n;
   int grid = d.num_sms > 0 ? d.num_sms : 148;
-  if (grid > num_tiles) grid = num_tiles;
+  if (pair) {
+    grid &= ~1;
+    if (grid > 2 * num_tiles) grid = 2 * num_tiles;
+  } else if (grid > num_tiles) {
+    grid = num_tiles;
+  }
   // epilogue tensors: 32-row x 64-column boxes (one per epilogue warp and step)
   if (d.out != nullptr) {
     if ((rc = make_map_bf16(&mo, d.out, d.M, d.N, d.ldo, 32)) != 0) return rc * 10 - 5;
@@ -368,19 +439,20 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
     mo = a0;
   }
   mx = a0;
-  cudaError_t e;
   switch (d.epi) {
-    case EPI_NONE: e = launch_epi<EPI_NONE>(a0, b0, a1, b1, mo, mx, args, grid, st); break;
+    case EPI_NONE: break;
     case EPI_GELU:
       if (d.out2 == nullptr) return -13;
       if ((rc = make_map_bf16(&mx, d.out2, d.M, d.N, d.ldo2, 32)) != 0) return rc * 10 - 6;
-      e = launch_epi<EPI_GELU>(a0, b0, a1, b1, mo, mx, args, grid, st); break;
+      break;
     case EPI_DGELU:
       if (d.aux == nullptr) return -14;
       if ((rc = make_map_bf16(&mx, d.aux, d.M, d.N, d.ldaux, 32)) != 0) return rc * 10 - 7;
-      e = launch_epi<EPI_DGELU>(a0, b0, a1, b1, mo, mx, args, grid, st); break;
+      break;
     default: return -15;
   }
+  const cudaError_t e = pair ? launch_kind<true>(d.epi, a0, b0, a1, b1, mo, mx, args, grid, st)
+                             : launch_kind<false>(d.epi, a0, b0, a1, b1, mo, mx, args, grid, st);
   return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
 }
 

@@ -36,6 +36,7 @@ struct GemmDesc {
   const __nv_bfloat16* aux; int ldaux;
   int epi;
   int num_sms;
+  int pair;   // 1: CTA pairs (cta_group::2, 256 x 256 tiles); 0: single-CTA 128 x 256 tiles
 };
 
 int gemm_cp_launch(const GemmDesc& d, cudaStream_t st);

@@ -13,6 +13,7 @@ from . import _lib as L
 BF16, F32 = torch.bfloat16, torch.float32
 launch_count = 0  # number of cara_* kernel launches issued (bench.py reports it as gpu_launches)
 param_generation = 0  # bumped by adamw_step: parameters changed behind autograd's version counters
+gemm_pair = int(__import__('os').environ.get('CARA_GEMM_PAIR', '0'))  # 1: experimental tcgen05 cta_group::2 tiles (slower so far)
 gemm_events = None  # bench.py: list of (start event, end event, algorithmic flops) per fused-projection launch
 _dev = [None]
 
@@ -38,7 +39,7 @@ def round_rank(r):
 
 
 def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, out=None, out2=None, aux=None,
-            want_pre=True, num_sms=0):
+            want_pre=True, num_sms=0, pair=None):
     """out[M,N] = a0[M,K0] b0[N,K0]^T + bias (+ adapter segment a1/b1), see cara_gemm_cp."""
     st = _prep(a0)
     M, K0 = a0.shape
@@ -69,6 +70,7 @@ def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, o
         assert aux is not None and aux.dtype == BF16 and aux.shape == (M, N)
         d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
     d.epi, d.num_sms = epi, num_sms
+    d.pair = gemm_pair if pair is None else int(pair)
     if gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -51,6 +51,7 @@ typedef struct cara_gemm_desc {
   const void* aux; int ldaux;
   int epi;
   int num_sms; /* 0 = all */
+  int pair;    /* 0 = single-CTA 128x256 tiles (default); 1 = experimental CTA pairs (tcgen05 cta_group::2, 256x256 tiles) */
 } cara_gemm_desc;
 CARA_API int cara_gemm_cp(const cara_gemm_desc* d, void* stream);
 

@@ -45,6 +45,7 @@ def run(M, N, K0, K1=0, slices=1, bias=False, epi=L.EPI_NONE, seed=0, time_it=Fa
         torch.nn.functional.gelu(u).sum().backward()
         ref = ref * u.grad
     d.epi = epi
+    d.pair = int(os.environ.get('CARA_GEMM_PAIR', '0'))
     st = torch.cuda.current_stream().cuda_stream
     L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
     torch.cuda.synchronize()
