@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -452,8 +453,23 @@ int bwd_t(const AttnArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+// CARA_ATTN_TC (default 3): bit 0 = tcgen05 forward, bit 1 = tcgen05 backward (D = 64, N <= 256); other shapes and
+// cleared bits run the mma.sync kernels above.
+static int attn_tc_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CARA_ATTN_TC");
+    v = e != nullptr ? atoi(e) : 3;
+  }
+  return v;
+}
+
 int attn_fwd_launch(const AttnArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.N <= 0 || a.H <= 0) return -50;
+  if (attn_tc_mask() & 1) {
+    const int rc = attn_fwd_tc_launch(a, st);
+    if (rc <= 0) return rc;
+  }
   if (a.D == 64) return fwd_t<64>(a, st);
   if (a.D == 80) return fwd_t<80>(a, st);
   return -50;

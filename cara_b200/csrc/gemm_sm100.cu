@@ -341,7 +341,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // Row-major bf16 [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-B swizzle.
-static int make_map_bf16(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
+int make_map_bf16(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return -1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) return -2;

@@ -1,5 +1,6 @@
 // Internal interface of the tcgen05 fused-projection GEMM (see gemm_sm100.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -40,5 +41,9 @@ struct GemmDesc {
 };
 
 int gemm_cp_launch(const GemmDesc& d, cudaStream_t st);
+
+// TMA descriptor of a row-major bf16 [rows, cols] matrix (row pitch ld elements): box = [box_rows, 64 columns],
+// 128-byte swizzle.  0 on success.
+int make_map_bf16(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows);
 
 }  // namespace cara

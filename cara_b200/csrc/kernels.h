@@ -49,6 +49,8 @@ struct AttnArgs {
 };
 int attn_fwd_launch(const AttnArgs& a, cudaStream_t st);
 int attn_bwd_launch(const AttnArgs& a, cudaStream_t st);
+// tcgen05 variants (attention_tc.cu): 0 = launched, 1 = shape not covered (D != 64 or N > 256), < 0 = error
+int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st);
 
 // misc.cu
 int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S, int P, int Kp, cudaStream_t st);
