@@ -20,8 +20,14 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _extra_flags():
+    """Extra nvcc flags for experiments, e.g. CARA_NVCC_EXTRA=-DCARA_ATTN_DEBUG (cycle stamps in the attention kernels)."""
+    return os.environ.get("CARA_NVCC_EXTRA", "").split()
+
+
 def _digest():
     h = hashlib.sha256()
+    h.update(" ".join(_extra_flags()).encode())
     files = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
                    glob.glob(os.path.join(CSRC, "*.h")) +
                    glob.glob(os.path.join(HERE, "..", "include", "*.h")) + [os.path.abspath(__file__)])
@@ -39,7 +45,7 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + _extra_flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -95,16 +95,17 @@ int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, lon
 int cara_attn_fwd(const void* qkv, void* o, void* o_lo, float* lse, int B, int N, int H, int D, float scale,
                   void* stream) {
   cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(o), static_cast<bf16*>(o_lo), lse, nullptr,
-                   nullptr, B, N, H, D, scale};
+                   nullptr, nullptr, B, N, H, D, scale};
   CARA_RET(cara::attn_fwd_launch(a, CARA_STREAM(stream)), "cara_attn_fwd");
 }
 int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float* lse, const void* d_o, void* dqkv,
-                  int B, int N, int H, int D, float scale, void* stream) {
+                  float* delta_ws, int B, int N, int H, int D, float scale, void* stream) {
   cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(const_cast<void*>(o)),
                    static_cast<bf16*>(const_cast<void*>(o_lo)), const_cast<float*>(lse),
-                   static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), B, N, H, D, scale};
+                   static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), delta_ws, B, N, H, D, scale};
   CARA_RET(cara::attn_bwd_launch(a, CARA_STREAM(stream)), "cara_attn_bwd");
 }
+int cara_debug_read(long long* out, int n) { return cara::attn_debug_read(out, n); }
 int cara_patchify(const float* img, void* patches, int B, int Cin, int S, int P, int Kp, void* stream) {
   CARA_RET(cara::patchify_launch(img, static_cast<bf16*>(patches), B, Cin, S, P, Kp, CARA_STREAM(stream)), "cara_patchify");
 }

@@ -476,6 +476,10 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t st) {
 }
 int attn_bwd_launch(const AttnArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.N <= 0 || a.H <= 0 || a.o_lo == nullptr) return -50;
+  if (attn_tc_mask() & 2) {
+    const int rc = attn_bwd_tc_launch(a, st);
+    if (rc <= 0) return rc;
+  }
   if (a.D == 64) return bwd_t<64>(a, st);
   if (a.D == 80) return bwd_t<80>(a, st);
   return -50;

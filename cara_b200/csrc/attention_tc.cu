@@ -206,6 +206,327 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a
   }
 }
 
+
+// ------------------------------------------------------------------------------------ backward
+// Pre-pass (HBM-bound, one warp per token row): delta[b,h,n] = sum_d dO[n,h,d] (O + O_lo)[n,h,d].
+// O is carried as a bf16 (hi, lo) pair because with plain bf16 O the rows of dS stop summing to ~0 for peaked
+// softmax rows and dq / dk lose the parity bar.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o,
+                  const __nv_bfloat16* __restrict__ o_lo, float* __restrict__ delta, int rows, int N, int H) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / N, n = row % N;
+  const long base = static_cast<long>(row) * H * TC_D;
+  for (int i = lane; i < H * 8; i += 32) {                       // 16-byte chunk i: head i / 8
+    const uint4 x = *reinterpret_cast<const uint4*>(d_o + base + i * 8);
+    const uint4 y = *reinterpret_cast<const uint4*>(o + base + i * 8);
+    const uint4 z = *reinterpret_cast<const uint4*>(o_lo + base + i * 8);
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w}, zw[4] = {z.x, z.y, z.z, z.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 xf = unpack_bf16(xw[e]), yf = unpack_bf16(yw[e]), zf = unpack_bf16(zw[e]);
+      acc += xf.x * (yf.x + zf.x) + xf.y * (yf.y + zf.y);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if ((lane & 7) == 0) delta[(static_cast<long>(b) * H + (i >> 3)) * N + n] = acc;
+  }
+}
+
+// One persistent CTA per SM walks over (sample, head) pairs.  Per head and 128-key tile t (keys on the TMEM lanes):
+//   S^T  = K_t Q^T            -> TMEM [0, npad)            (both operands K-major from smem)
+//   dP^T = V_t dO^T           -> TMEM [256, 256 + npad)
+//   threads (lane = key, two warps per lane quarter splitting the query columns):
+//        P^T  = 2^(S^T sl2 - lse[q])                 -> bf16 back into TMEM over the scores it replaces
+//        dS^T = P^T (.) (dP^T - delta[q])            -> bf16 into ONE shared tile laid out [64-query block][key][128 B]
+//   dV_t  = P^T dO            A = P^T from TMEM,  B = dO as it lies in memory (MN-major)          -> TMEM [256, 320)
+//   dK_t  = dS^T Q            A = the shared tile read K-major,  B = Q (MN-major)                 -> TMEM [320, 384)
+//   dQ   += dS K_t            A = THE SAME shared tile read MN-major (M = query), B = K_t (MN-major) -> TMEM [384, 512)
+// so the [N, N] matrices never leave the SM, nothing is transposed by the SIMT cores, and the only shared-memory
+// staging is the single dS^T tile.  dQ partials of the two key tiles are summed in registers.
+constexpr int TCB_THREADS = 288;         // warps 0-7: compute (lane quarter = warp & 3, column half = warp >> 2); warp 8: TMA + MMA
+constexpr int TCB_DS_BYTES = 65536;      // 4 query blocks x 128 keys x 128 B
+constexpr int TCB_DP_COL = 256, TCB_DV_COL = 256, TCB_DK_COL = 320, TCB_DQ_COL = 384;
+
+__device__ long long g_attn_dbg[64];
+#ifdef CARA_ATTN_DEBUG
+#define DBG_STAMP(i) do { if (blockIdx.x == 0 && (i) < 64) g_attn_dbg[(i)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ void named_bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TCB_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                   const AttnArgs a, const int npad) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tile0 = (raw + 1023u) & ~1023u;
+  const uint32_t tile_bytes = static_cast<uint32_t>(npad) * 128u;
+  const uint32_t sQ = tile0, sK = sQ + tile_bytes, sV = sK + tile_bytes, sDO = sV + tile_bytes;
+  // the second key tile's A operands read 128 rows from row 128 of sK / sV whatever npad is: what lies behind
+  // them (sV, sDO, then the dS^T tile) is allocated and always holds finite bf16 data
+  const uint32_t sDS = sDO + tile_bytes;
+  const uint32_t stats = sDS + TCB_DS_BYTES;                 // nlse[256], delta[256] (fp32)
+  const uint32_t bars = stats + 2048u;
+  const uint32_t bar_in = bars, bar_sdp = bars + 8, bar_pds = bars + 16, bar_kv = bars + 24, bar_out = bars + 32,
+                 bar_rd = bars + 40, tmem_slot = bars + 48;
+  float* s_nlse = reinterpret_cast<float*>(smem_raw + (stats - raw));
+  float* s_delta = s_nlse + 256;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, C = a.H * TC_D;
+  const int nt = (N + 127) / 128;                              // key tiles == query tiles
+  const int ksteps = npad / 16;
+  const int c_split = ((ksteps + 1) / 2) * 16;                 // query columns [0, c_split) | [c_split, npad)
+  const int heads = a.B * a.H;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+      mbar_init(bar_in, 1);
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, 256);
+      mbar_init(bar_kv, 1);
+      mbar_init(bar_out, 1);
+      mbar_init(bar_rd, 256);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else {
+    // the dS^T tile may be read (as don't-care rows / columns) before it is ever written: make it finite
+    for (uint32_t off = threadIdx.x * 16u; off < TCB_DS_BYTES; off += 256u * 16u)
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sDS + off), "r"(0u) : "memory");
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      auto issue_loads = [&](int head) {
+        const int b = head / a.H, h = head % a.H;
+        const int row0 = b * N;
+        mbar_expect_tx(bar_in, 4u * tile_bytes);
+        tma_load_2d(sK, &map_qkv, bar_in, C + h * TC_D, row0);
+        tma_load_2d(sQ, &map_qkv, bar_in, h * TC_D, row0);
+        tma_load_2d(sV, &map_qkv, bar_in, 2 * C + h * TC_D, row0);
+        tma_load_2d(sDO, &map_do, bar_in, h * TC_D, row0);
+      };
+      const uint32_t idesc_s = umma_idesc_bf16_major(128, npad, 0, 0);
+      constexpr uint32_t idesc_dv = umma_idesc_bf16_major(128, TC_D, 0, 1);   // A from TMEM (K-major), B MN-major
+      constexpr uint32_t idesc_dk = umma_idesc_bf16_major(128, TC_D, 0, 1);   // A K-major smem, B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc_bf16_major(128, TC_D, 1, 1);   // A MN-major smem, B MN-major
+      uint32_t it = 0, n = 0;
+      if (static_cast<int>(blockIdx.x) < heads) issue_loads(blockIdx.x);
+      for (int head = blockIdx.x; head < heads; head += gridDim.x, ++it) {
+        mbar_wait(bar_in, it & 1u);
+        if (it == 1) DBG_STAMP(0);
+        for (int t = 0; t < nt; ++t, ++n) {
+          if (n > 0) mbar_wait(bar_rd, (n - 1u) & 1u);         // previous outputs have been read out of TMEM
+          tc_fence_after();
+          if (it == 1) DBG_STAMP(1 + 8 * t);
+          {
+            const uint64_t dk = umma_desc_sw128(sK + static_cast<uint32_t>(t) * 16384u), dq = umma_desc_sw128(sQ);
+            const uint64_t dv = umma_desc_sw128(sV + static_cast<uint32_t>(t) * 16384u), dd = umma_desc_sw128(sDO);
+#pragma unroll
+            for (int k = 0; k < TC_D / 16; ++k) umma_bf16(tmem_base, dk + 2u * k, dq + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < TC_D / 16; ++k)
+              umma_bf16(tmem_base + TCB_DP_COL, dv + 2u * k, dd + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_sdp);
+          mbar_wait(bar_pds, n & 1u);                           // P^T is in TMEM, dS^T in shared memory
+          tc_fence_after();
+          if (it == 1) DBG_STAMP(2 + 8 * t);
+          for (int j = 0; j < ksteps; ++j) {                    // dV_t = P^T dO   (K = queries)
+            const uint32_t pcol = 16 * j < c_split ? 8u * j : static_cast<uint32_t>(c_split + 8 * (j - c_split / 16));
+            umma_bf16_ts(tmem_base + TCB_DV_COL, tmem_base + pcol,
+                         umma_desc_mn_sw128(sDO + static_cast<uint32_t>(j) * 2048u, tile_bytes, 1024u), idesc_dv,
+                         j != 0 ? 1u : 0u);
+          }
+          for (int j = 0; j < ksteps; ++j) {                    // dK_t = dS^T Q   (K = queries)
+            umma_bf16(tmem_base + TCB_DK_COL,
+                      umma_desc_sw128(sDS + static_cast<uint32_t>(j >> 2) * 16384u + static_cast<uint32_t>(j & 3) * 32u),
+                      umma_desc_mn_sw128(sQ + static_cast<uint32_t>(j) * 2048u, tile_bytes, 1024u), idesc_dk,
+                      j != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_kv);                                  // dK_t / dV_t can be read out while dQ still runs
+          const int kk = (npad - 128 * t < 128 ? npad - 128 * t : 128) / 16;   // valid keys of this tile / 16
+          for (int m = 0; m < nt; ++m) {                        // dQ_m = dS K_t   (K = keys of tile t)
+            for (int j = 0; j < kk; ++j) {
+              umma_bf16(tmem_base + TCB_DQ_COL + 64u * m,
+                        umma_desc_mn_sw128(sDS + static_cast<uint32_t>(2 * m) * 16384u + static_cast<uint32_t>(j) * 2048u,
+                                           16384u, 1024u),
+                        umma_desc_mn_sw128(sK + static_cast<uint32_t>(t) * 16384u + static_cast<uint32_t>(j) * 2048u,
+                                           tile_bytes, 1024u),
+                        idesc_dq, j != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_out);
+          if (it == 1) DBG_STAMP(3 + 8 * t);
+        }
+        // every MMA that reads this head's tiles has been issued; once they retire the next head may land
+        mbar_wait(bar_out, (n - 1u) & 1u);
+        if (it == 1) DBG_STAMP(20);
+        if (head + static_cast<int>(gridDim.x) < heads) issue_loads(head + gridDim.x);
+      }
+    }
+  } else {
+    const int q4 = warp & 3, half = warp >> 2;
+    const int tid = threadIdx.x;                                // 0..255
+    const int key_local = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    const float sl2 = a.scale * 1.4426950408889634f;
+    const int c_begin = half == 0 ? 0 : c_split, c_end = half == 0 ? c_split : npad;
+    const uint32_t ds_row = sDS + static_cast<uint32_t>(key_local) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(key_local & 7);
+    uint32_t n = 0, it = 0;
+    for (int head = blockIdx.x; head < heads; head += gridDim.x, ++it) {
+      const int b = head / a.H, h = head % a.H;
+      // ---- per-head statistics (everyone is past the previous head's last use of them: see bar_pds / bar_out)
+      {
+        const long sb = (static_cast<long>(b) * a.H + h) * N;
+        s_nlse[tid] = tid < N ? -a.lse[sb + tid] : -1e30f;
+        s_delta[tid] = tid < N ? a.delta[sb + tid] : 0.f;
+        named_bar_sync_256();
+      }
+      if (it == 1 && tid == 0) DBG_STAMP(32);
+      float dq[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) dq[j] = 0.f;
+      __nv_bfloat16* gbase = a.dqkv + static_cast<long>(b) * N * 3 * C + h * TC_D;
+
+      for (int t = 0; t < nt; ++t, ++n) {
+        const int key = t * 128 + key_local;
+        const bool key_ok = key < N;
+        const bool warp_live = t * 128 + q4 * 32 < npad;        // warp-uniform
+        mbar_wait(bar_sdp, n & 1u);
+        tc_fence_after();
+        if (it == 1 && tid == 0) DBG_STAMP(33 + 8 * t);
+        if (warp_live) {
+          for (int c = c_begin; c < c_end; c += 16) {
+            uint32_t s[16], dp[16], pk[8], dsk[8];
+            tmem_ld16(lane_addr + c, s);
+            tmem_ld16(lane_addr + TCB_DP_COL + c, dp);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 L = *reinterpret_cast<const float4*>(s_nlse + c + 4 * j4);
+              const float4 Dl = *reinterpret_cast<const float4*>(s_delta + c + 4 * j4);
+              const float p0 = exp2f(fmaf(__uint_as_float(s[4 * j4 + 0]), sl2, L.x));
+              const float p1 = exp2f(fmaf(__uint_as_float(s[4 * j4 + 1]), sl2, L.y));
+              const float p2 = exp2f(fmaf(__uint_as_float(s[4 * j4 + 2]), sl2, L.z));
+              const float p3 = exp2f(fmaf(__uint_as_float(s[4 * j4 + 3]), sl2, L.w));
+              const float d0 = p0 * (__uint_as_float(dp[4 * j4 + 0]) - Dl.x);
+              const float d1 = p1 * (__uint_as_float(dp[4 * j4 + 1]) - Dl.y);
+              const float d2 = p2 * (__uint_as_float(dp[4 * j4 + 2]) - Dl.z);
+              const float d3 = p3 * (__uint_as_float(dp[4 * j4 + 3]) - Dl.w);
+              pk[2 * j4] = pack_bf16(p0, p1); pk[2 * j4 + 1] = pack_bf16(p2, p3);
+              dsk[2 * j4] = pack_bf16(d0, d1); dsk[2 * j4 + 1] = pack_bf16(d2, d3);
+            }
+            // P^T: 16 queries of this key -> 8 packed columns on top of already consumed scores
+            tmem_st8(lane_addr + (half == 0 ? (c >> 1) : c_split + ((c - c_split) >> 1)), pk);
+            // dS^T: two 16-byte chunks of row `key_local` in query block c / 64
+            const uint32_t blk = ds_row + static_cast<uint32_t>(c >> 6) * 16384u;
+            const uint32_t ch = static_cast<uint32_t>((c & 63) >> 3);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + ((ch ^ sw) << 4)), "r"(dsk[0]), "r"(dsk[1]),
+                         "r"(dsk[2]), "r"(dsk[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((ch + 1u) ^ sw) << 4)), "r"(dsk[4]),
+                         "r"(dsk[5]), "r"(dsk[6]), "r"(dsk[7]) : "memory");
+          }
+          // keys in [N, npad) are padding: their rows of dS^T feed dQ and must be exactly zero (their scores are
+          // finite garbage -- the next sample's rows -- so the values written above may be anything, even inf/nan)
+          if (!key_ok) {
+            for (int c = c_begin; c < c_end; c += 8) {
+              const uint32_t blk = ds_row + static_cast<uint32_t>(c >> 6) * 16384u;
+              const uint32_t ch = static_cast<uint32_t>((c & 63) >> 3);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(blk + ((ch ^ sw) << 4)), "r"(0u) : "memory");
+            }
+          }
+          tmem_st_wait();
+          fence_proxy_async();                                  // dS^T stores -> visible to the tensor core (async proxy)
+        }
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+        if (it == 1 && tid == 0) DBG_STAMP(34 + 8 * t);
+        // ---- read out: half 0 -> dK_t rows, half 1 -> dV_t rows (while the dQ MMAs are still running)
+        mbar_wait(bar_kv, n & 1u);
+        tc_fence_after();
+        if (it == 1 && tid == 0) DBG_STAMP(35 + 8 * t);
+        if (warp_live) {
+          const uint32_t col = half == 0 ? TCB_DK_COL : TCB_DV_COL;
+          const float sc = half == 0 ? a.scale : 1.0f;
+          uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<long>(key) * 3 * C + (half == 0 ? C : 2 * C));
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            uint32_t r[32];
+            tmem_ld32(lane_addr + col + 32 * part, r);
+            tmem_ld_wait();
+            if (key_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                dst[4 * part + j] =
+                    make_uint4(pack_bf16(__uint_as_float(r[8 * j + 0]) * sc, __uint_as_float(r[8 * j + 1]) * sc),
+                               pack_bf16(__uint_as_float(r[8 * j + 2]) * sc, __uint_as_float(r[8 * j + 3]) * sc),
+                               pack_bf16(__uint_as_float(r[8 * j + 4]) * sc, __uint_as_float(r[8 * j + 5]) * sc),
+                               pack_bf16(__uint_as_float(r[8 * j + 6]) * sc, __uint_as_float(r[8 * j + 7]) * sc));
+              }
+            }
+          }
+        }
+        // ---- dQ partial of query tile `half` (lane = query) accumulated over the key tiles in registers
+        mbar_wait(bar_out, n & 1u);
+        tc_fence_after();
+        if (it == 1 && tid == 0) DBG_STAMP(36 + 8 * t);
+        if (half < nt) {
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            uint32_t r[32];
+            tmem_ld32(lane_addr + TCB_DQ_COL + 64 * half + 32 * part, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dq[32 * part + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_rd);
+        if (it == 1 && tid == 0) DBG_STAMP(37 + 8 * t);
+      }
+      // ---- dQ rows of query tile `half`
+      const int qrow = half * 128 + key_local;
+      if (half < nt && qrow < N) {
+        uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<long>(qrow) * 3 * C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dst[j] = make_uint4(pack_bf16(dq[8 * j + 0] * a.scale, dq[8 * j + 1] * a.scale),
+                              pack_bf16(dq[8 * j + 2] * a.scale, dq[8 * j + 3] * a.scale),
+                              pack_bf16(dq[8 * j + 4] * a.scale, dq[8 * j + 5] * a.scale),
+                              pack_bf16(dq[8 * j + 6] * a.scale, dq[8 * j + 7] * a.scale));
+        }
+      }
+      if (it == 1 && tid == 0) DBG_STAMP(60);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 // D = 64, N <= 256: tcgen05 path.  Returns 1 when the shape is not covered (caller falls back to the mma.sync kernel).
@@ -230,4 +551,33 @@ int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? 0 : -53;
 }
 
+}  // namespace cara
+
+namespace cara {
+int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
+  if (a.D != TC_D || a.N > 256 || a.N < 1 || a.delta == nullptr) return 1;
+  const int npad = ((a.N + 15) / 16) * 16;
+  const long rows = static_cast<long>(a.B) * a.N;
+  const long C = static_cast<long>(a.H) * TC_D;
+  CUtensorMap map_qkv, map_do;
+  if (make_map_bf16(&map_qkv, a.qkv, rows, 3 * C, 3 * C, npad) != 0) return -54;
+  if (make_map_bf16(&map_do, a.d_o, rows, C, C, npad) != 0) return -54;
+  const int smem = 1024 + 4 * npad * 128 + TCB_DS_BYTES + 2048 + 64;
+  static int configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -52;
+    configured = smem;
+  }
+  int grid = a.B * a.H;
+  if (grid > 148) grid = 148;
+  attn_delta_kernel<<<static_cast<int>((rows + 7) / 8), 256, 0, st>>>(a.d_o, a.o, a.o_lo, a.delta, static_cast<int>(rows),
+                                                                     a.N, a.H);
+  attn_bwd_tc_kernel<<<grid, TCB_THREADS, smem, st>>>(map_qkv, map_do, a, npad);
+  return cudaGetLastError() == cudaSuccess ? 0 : -53;
+}
+int attn_debug_read(long long* out, int n) {
+  if (n > 64) n = 64;
+  if (n <= 0 || cudaMemcpyFromSymbol(out, g_attn_dbg, sizeof(long long) * n) != cudaSuccess) return 0;
+  return n;
+}
 }  // namespace cara

@@ -45,12 +45,15 @@ int cols_launch(const ColsArgs& a, int rp, int num_sms, cudaStream_t st);
 struct AttnArgs {
   const __nv_bfloat16* qkv; __nv_bfloat16* o; __nv_bfloat16* o_lo; float* lse;   // lse [B, H, N] (log2 domain)
   const __nv_bfloat16* d_o; __nv_bfloat16* dqkv;                // backward only
+  float* delta;                                                 // backward workspace [B, H, N] fp32 (tcgen05 path)
   int B, N, H, D; float scale;
 };
+int attn_debug_read(long long* out, int n);
 int attn_fwd_launch(const AttnArgs& a, cudaStream_t st);
 int attn_bwd_launch(const AttnArgs& a, cudaStream_t st);
 // tcgen05 variants (attention_tc.cu): 0 = launched, 1 = shape not covered (D != 64 or N > 256), < 0 = error
 int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st);
+int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st);
 
 // misc.cu
 int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S, int P, int Kp, cudaStream_t st);

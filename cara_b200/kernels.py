@@ -186,8 +186,9 @@ def attn_bwd(qkv, o, o_lo, lse, d_o, B, N, H, D, scale):
     st = _prep(qkv)
     assert d_o.is_contiguous() and d_o.dtype == BF16
     dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, N), device=qkv.device, dtype=F32)
     L.check(L.lib().cara_attn_bwd(qkv.data_ptr(), o.data_ptr(), o_lo.data_ptr(), lse.data_ptr(), d_o.data_ptr(),
-                                  dqkv.data_ptr(), B, N, H, D, scale, st), "cara_attn_bwd")
+                                  dqkv.data_ptr(), delta.data_ptr(), B, N, H, D, scale, st), "cara_attn_bwd")
     return dqkv
 
 

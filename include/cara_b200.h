@@ -97,8 +97,12 @@ CARA_API int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const voi
  * D in {64,80}. */
 CARA_API int cara_attn_fwd(const void* qkv, void* o, void* o_lo, float* lse, int B, int N, int H, int D,
                            float scale, void* stream);
+/* delta_ws: caller-provided fp32 workspace [B,H,N] (rowsum(dO (.) O), written by a streaming pre-pass). */
 CARA_API int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float* lse, const void* d_o,
-                           void* dqkv, int B, int N, int H, int D, float scale, void* stream);
+                           void* dqkv, float* delta_ws, int B, int N, int H, int D, float scale, void* stream);
+/* Profiling aid: copies up to n device-side cycle stamps recorded by the attention kernels (debug builds of the
+ * kernels only write them for CTA 0); returns the number of values copied. */
+CARA_API int cara_debug_read(long long* out, int n);
 
 /* timm PatchEmbed (conv PxP stride P) as im2col: img fp32 [B,Cin,S,S] -> bf16 [B*(S/P)^2, Kp] (zero padded),
  * then cara_gemm_cp against the flattened conv weight, then token assembly with cls/pos into the fp32

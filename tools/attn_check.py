@@ -51,3 +51,11 @@ if __name__ == "__main__":
     for shp in [(1, 128, 1, 64), (1, 64, 2, 64), (2, 17, 3, 64), (1, 50, 2, 64), (3, 197, 12, 64), (2, 256, 2, 64), (1, 200, 3, 64)]:
         check(*shp, bwd=bwd)
     timeit(256, 197, 12, 64, bwd=bwd)
+    import ctypes as C
+    from cara_b200 import _lib as L
+    buf = (C.c_longlong * 64)()
+    if L.lib().cara_debug_read(buf, 64) and buf[0]:
+        v = list(buf)
+        base = v[0]
+        print("control: in->%s" % [(i, v[i] - base) for i in (1, 2, 3, 9, 10, 11, 20) if v[i]])
+        print("compute: %s" % [(i, v[i] - base) for i in range(32, 64) if v[i]])
