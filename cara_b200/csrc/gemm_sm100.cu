@@ -14,12 +14,16 @@
 // columns) for the GELU / GELU' epilogues whose per-element math would otherwise outlast the K = 768 main
 // loop.  Two 256-column fp32 accumulators in TMEM let the epilogue of tile i overlap the main loop of tile
 // i+1.  Epilogue data path: tcgen05.ld -> registers (bias / GELU / GELU') -> 128-byte-swizzled shared
-// staging (conflict-free 16-byte accesses) -> TMA tensor store, 32 rows x 64 columns per warp and step;
-// the GELU' operand arrives the same way through TMA loads prefetched one step ahead and is overwritten in
-// place by the result.  HBM therefore only ever sees full 128-byte lines.
+// staging (conflict-free 16-byte accesses) -> TMA tensor store, 32 rows x 64 columns per warp and step, so HBM
+// only ever sees full 128-byte lines.  Every kind stages through 32 KB (plain: two 4 KB buffers for each of 4
+// warps; GELU kinds: one buffer for each of 8 warps, the two GELU outputs going through it one after the other)
+// which leaves room for a 4-stage main-loop ring in all of them.  The GELU' operand (saved pre-activation) is read
+// with plain 16-byte loads: one full 128-byte line per thread and step.
 #include "ptx.cuh"
 #include "gemm_sm100.h"
 #include "mathfn.cuh"
+
+#include <stdlib.h>
 
 namespace cara {
 
@@ -38,16 +42,17 @@ constexpr int EBUF = 32 * EC * 2;               // 4 KB staging buffer: 32 rows 
 // (measured: the GELU kinds are bound by main-loop ring depth, not by epilogue math -- 3 stages + 8 epilogue
 // warps ran at 288 us where 4 stages + 4 warps ... see profiles/)
 __host__ __device__ constexpr int num_stages(int epi, bool pair) { return pair ? 6 : 4; }
-__host__ __device__ constexpr int num_epi_warps(int epi) { return epi == EPI_DGELU ? 8 : 4; }
+__host__ __device__ constexpr int num_epi_warps(int epi) { return epi == EPI_NONE ? 4 : 8; }
+__host__ __device__ constexpr int epi_bufs(int epi) { return epi == EPI_NONE ? 2 : 1; }   // staging buffers per warp
 __host__ __device__ constexpr int num_threads(int epi) { return 64 + 32 * num_epi_warps(epi); }
 __host__ __device__ constexpr int gemm_smem(int epi, bool pair) {
   int stages = num_stages(epi, pair);
-  while (stages * stage_bytes(pair) + num_epi_warps(epi) * 2 * EBUF + 1024 + 512 > 227 * 1024) --stages;
-  return stages * stage_bytes(pair) + num_epi_warps(epi) * 2 * EBUF + 1024 /*align slack*/ + 512 /*barriers*/;
+  while (stages * stage_bytes(pair) + num_epi_warps(epi) * epi_bufs(epi) * EBUF + 1024 + 512 > 227 * 1024) --stages;
+  return stages * stage_bytes(pair) + num_epi_warps(epi) * epi_bufs(epi) * EBUF + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 __host__ __device__ constexpr int fitted_stages(int epi, bool pair) {
   int stages = num_stages(epi, pair);
-  while (stages * stage_bytes(pair) + num_epi_warps(epi) * 2 * EBUF + 1024 + 512 > 227 * 1024) --stages;
+  while (stages * stage_bytes(pair) + num_epi_warps(epi) * epi_bufs(epi) * EBUF + 1024 + 512 > 227 * 1024) --stages;
   return stages;
 }
 
@@ -74,9 +79,10 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-B alignment
-  const uint32_t stage_out = tiles + STAGES * STAGE_BYTES; // [EW warps][2 buffers][4 KB]
-  const uint32_t bars = stage_out + EW * 2 * EBUF;
-  // barrier map (8 B each): full[S], empty[S], tfull[2], tempty[2], aux[EW warps][2], then the TMEM base word
+  constexpr int EBUFS = epi_bufs(EPI);
+  const uint32_t stage_out = tiles + STAGES * STAGE_BYTES; // [EW warps][EBUFS buffers][4 KB]
+  const uint32_t bars = stage_out + EW * EBUFS * EBUF;
+  // barrier map (8 B each): full[S], empty[S], tfull[2], tempty[2], (unused)[EW warps][2], then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
@@ -100,7 +106,9 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tma_prefetch_desc(&mapB1);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), PAIR ? 2 : 1);      // pair: leader's arrive.expect_tx + the peer producer's arrive
+      // pair: only the leader arrives (expect_tx of BOTH CTAs' bytes); the peer's TMA loads complete_tx on the
+      // leader's barrier directly and the peer cannot run a phase ahead (its stage is freed by the leader's commit)
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -132,7 +140,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
         if (PAIR) tma_load_2d_pair(dst, m, bar, c0, c1); else tma_load_2d(dst, m, bar, c0, c1);
       };
-      for (int t = unit; t < num_tiles; t += nunits) {
+      for (int t = unit; t < num_tiles && !(p.debug & 2); t += nunits) {
         const TileCoord tc = tile_coord(t);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);       // own stage free (pair: the leader's commit is multicast to both)
@@ -149,7 +157,6 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             load(sa, &mapA1, full_bar(s), slice * p.ext_rp + e * BK, tc.m0);
             load(sb, &mapB1, full_bar(s), e * BK, tc.n0 - slice * p.ext_slice_w + b_off);
           }
-          if (PAIR && rank != 0) mbar_arrive_remote(full_bar(s), 0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -167,7 +174,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(s), ph);             // TMA bytes have landed
+          if (!(p.debug & 2)) mbar_wait(full_bar(s), ph);   // TMA bytes have landed
           tc_fence_after();
           const uint32_t sa = tiles + s * STAGE_BYTES;
           const uint64_t da = umma_desc_sw128(sa);
@@ -198,49 +205,35 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int ew = warp - 2;                      // staging slot of this warp
     constexpr int NCH = (BN / EC) * 4 / EW;       // 64-column steps per warp and tile (4, or 2 with 8 warps)
     const int c_first = (ew >> 2) * NCH;          // with 8 warps the second four take the upper 128 columns
-    const uint32_t my_stage = stage_out + ew * (2 * EBUF);
+    const uint32_t my_stage = stage_out + ew * (EBUFS * EBUF);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);          // 128-B swizzle phase of this thread's row
     const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
     int as = 0;
     uint32_t aph = 0;
-    uint32_t q = 0;                               // running step counter of this warp (buffer / parity selector)
-    if (EPI == EPI_DGELU && lane == 0 && unit < num_tiles) {
-      const TileCoord t0 = tile_coord(unit);
-      mbar_expect_tx(aux_bar(ew, 0), EBUF);
-      tma_load_2d(my_stage, &mapAux, aux_bar(ew, 0), t0.n0 + c_first * EC, t0.m0 + lg * 32);
-    }
+    uint32_t q = 0;                               // running step counter of this warp (buffer selector)
+    auto stage_row = [&](uint32_t buf, const uint32_t (&w)[32]) { // this thread's 64 bf16 -> its swizzled staging row
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                     "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
+    };
     for (int t = unit; t < num_tiles; t += nunits) {
       const TileCoord tc = tile_coord(t);
+      const int grow = tc.m0 + lg * 32 + lane;    // global row of this thread
+      uint4 ux[8];                                // GELU': this thread's 64 saved pre-activations of the current step
+      if (EPI == EPI_DGELU) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow < p.M ? grow : 0) * p.ldaux +
+                                                          tc.n0 + c_first * EC);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ux[j] = __ldg(src + j);
+      }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci, ++q) {
         const int c = c_first + ci;
-        const uint32_t b = q & 1u;
-        // Staging use per kind.  NONE: out double-buffered in buf[b].  GELU: buf[0] = pre-activation,
-        // buf[1] = GELU output (single-buffered).  DGELU: buf[b] holds the TMA-loaded u tile and is
-        // overwritten in place by the result.
-        const uint32_t so = EPI == EPI_GELU ? my_stage : my_stage + b * EBUF;
-        const uint32_t sx = EPI == EPI_GELU ? my_stage + EBUF : so;
-        // earlier TMA stores must have finished READING the buffer(s) this step writes
-        if (lane == 0) {
-          if (EPI == EPI_NONE) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-        }
-        __syncwarp();
-        if (EPI == EPI_DGELU) {
-          if (lane == 0) {                                        // prefetch the next step's u tile
-            int nt = t, nci = ci + 1;
-            if (nci == NCH) { nt = t + nunits; nci = 0; }
-            if (nt < num_tiles) {
-              const TileCoord tn = tile_coord(nt);
-              mbar_expect_tx(aux_bar(ew, b ^ 1u), EBUF);
-              tma_load_2d(my_stage + (b ^ 1u) * EBUF, &mapAux, aux_bar(ew, b ^ 1u), tn.n0 + (c_first + nci) * EC,
-                          tn.m0 + lg * 32);
-            }
-          }
-          mbar_wait(aux_bar(ew, b), (q >> 1) & 1u);
-        }
+        const uint32_t buf = EBUFS == 2 ? my_stage + (q & 1u) * EBUF : my_stage;
         uint32_t r[64];
         tmem_ld32(t_row + c * EC, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         tmem_ld32(t_row + c * EC + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
@@ -252,6 +245,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (PAIR && rank != 0) mbar_arrive_remote(tempty_bar(as), 0); else mbar_arrive(tempty_bar(as));
           }
         }
+        if (p.debug & 1) continue;
         const int n = tc.n0 + c * EC;
         if (p.bias != nullptr && n < p.N) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
@@ -264,47 +258,59 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv.w);
           }
         }
+        uint32_t w0[32];                                          // first (or only) output of this step, packed bf16
+        if (EPI == EPI_DGELU) {
+          // dX through GELU: multiply by gelu'(u), u = saved fc1 pre-activation
+          const uint32_t* uw = reinterpret_cast<const uint32_t*>(ux);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                             // 8 x 16-byte chunks of this thread's row
-          const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
-          if (EPI == EPI_DGELU) {
-            // dX through GELU: multiply by gelu'(u), u = saved fc1 pre-activation (TMA-staged, same swizzle)
-            uint32_t u0, u1, u2, u3;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(sx + off));
-            const uint32_t uw[4] = {u0, u1, u2, u3};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16(uw[e]);
-              v[2 * e + 0] *= gelu_grad_fast(f.x);
-              v[2 * e + 1] *= gelu_grad_fast(f.y);
-            }
+          for (int j = 0; j < 32; ++j) {
+            const float2 f = unpack_bf16(uw[j]);
+            w0[j] = (p.debug & 8) ? pack_bf16(__uint_as_float(r[2 * j]) * f.x, __uint_as_float(r[2 * j + 1]) * f.y)
+                                  : pack_bf16(__uint_as_float(r[2 * j]) * gelu_grad_fast(f.x), __uint_as_float(r[2 * j + 1]) * gelu_grad_fast(f.y));
           }
-          const uint32_t o0 = pack_bf16(v[0], v[1]), o1 = pack_bf16(v[2], v[3]);
-          const uint32_t o2 = pack_bf16(v[4], v[5]), o3 = pack_bf16(v[6], v[7]);
-          if (p.out != nullptr)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(so + off), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-          if (EPI == EPI_GELU) {
-            // fc1: `out` keeps the pre-activation for backward, `out2` gets GELU(u) for fc2.  GELU is applied
-            // to the bf16-rounded pre-activation so forward and backward see the same u.
-            const uint32_t ow[4] = {o0, o1, o2, o3};
-            uint32_t gw[4];
+          if (ci + 1 < NCH) {                                     // next step's operand: in flight during the staging below
+            const uint4* src = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow < p.M ? grow : 0) * p.ldaux +
+                                                              n + EC);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16(ow[e]);
-              gw[e] = pack_bf16(gelu_fast(f.x), gelu_fast(f.y));
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sx + off), "r"(gw[0]), "r"(gw[1]), "r"(gw[2]), "r"(gw[3]) : "memory");
+            for (int j = 0; j < 8; ++j) ux[j] = __ldg(src + j);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w0[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        }
+        // earlier TMA stores must have finished READING the buffer this step writes
+        if (lane == 0) {
+          if (EBUFS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
+        __syncwarp();
+        if ((EPI != EPI_GELU || p.out != nullptr) && !(p.debug & 4)) {
+          stage_row(buf, w0);
+          fence_proxy_async();                                    // staging writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapOut, buf, n, tc.m0 + lg * 32);
+            tma_store_commit();
           }
         }
-        fence_proxy_async();                                      // staging writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          if (p.out != nullptr) tma_store_2d(&mapOut, so, n, tc.m0 + lg * 32);
-          if (EPI == EPI_GELU) tma_store_2d(&mapAux, sx, n, tc.m0 + lg * 32);
-          tma_store_commit();
+        if (EPI == EPI_GELU) {
+          // fc1: `out` keeps the pre-activation for backward, `out2` gets GELU(u) for fc2.  GELU is applied to the
+          // bf16-rounded pre-activation so forward and backward see the same u.  The math runs while the TMA engine
+          // is still reading the pre-activation out of the (single) staging buffer.
+          uint32_t w1[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 f = unpack_bf16(w0[j]);
+            w1[j] = (p.debug & 8) ? pack_bf16(f.x + 1.0f, f.y + 1.0f) : pack_bf16(gelu_fast(f.x), gelu_fast(f.y));
+          }
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          stage_row(buf, w1);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapAux, buf, n, tc.m0 + lg * 32);
+            tma_store_commit();
+          }
         }
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
@@ -421,6 +427,11 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   args.out = d.out; args.ldo = d.ldo;
   args.out2 = d.out2; args.ldo2 = d.ldo2;
   args.aux = d.aux; args.ldaux = d.ldaux;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("CARA_GEMM_DEBUG"); dbg = e != nullptr ? atoi(e) : 0; }
+    args.debug = dbg;
+  }
   const int tile_m = pair ? 2 * BM : BM;
   args.tiles_m = (d.M + tile_m - 1) / tile_m;
   args.tiles_n = (d.N + BN - 1) / BN;

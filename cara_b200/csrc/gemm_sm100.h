@@ -20,6 +20,7 @@ struct GemmArgs {
   __nv_bfloat16* out; int ldo;
   __nv_bfloat16* out2; int ldo2;
   const __nv_bfloat16* aux; int ldaux;
+  int debug;          // experiments (CARA_GEMM_DEBUG): 1 = epilogue only drains TMEM, 2 = no TMA loads / no full-barrier waits
 };
 
 // Host-side problem description.
