@@ -105,6 +105,13 @@ int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float*
                    static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), delta_ws, B, N, H, D, scale};
   CARA_RET(cara::attn_bwd_launch(a, CARA_STREAM(stream)), "cara_attn_bwd");
 }
+int cara_gelu_f32(const float* dy, const float* x, float* out, long n, void* stream) {
+  CARA_RET(cara::gelu_f32_launch(dy, x, out, n, CARA_STREAM(stream)), "cara_gelu_f32");
+}
+int cara_attn_f32(const float* qkv, float* o, float* lse, const float* d_o, float* dqkv, int B, int N, int H, int D,
+                  float scale, void* stream) {
+  CARA_RET(cara::attn_f32_launch(qkv, o, lse, d_o, dqkv, B, N, H, D, scale, CARA_STREAM(stream)), "cara_attn_f32");
+}
 int cara_debug_read(long long* out, int n) { return cara::attn_debug_read(out, n); }
 int cara_patchify(const float* img, void* patches, int B, int Cin, int S, int P, int Kp, void* stream) {
   CARA_RET(cara::patchify_launch(img, static_cast<bf16*>(patches), B, Cin, S, P, Kp, CARA_STREAM(stream)), "cara_patchify");

@@ -55,6 +55,11 @@ int attn_bwd_launch(const AttnArgs& a, cudaStream_t st);
 int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st);
 int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st);
 
+// fp32.cu: fp32 parity mode (exact-erf GELU forward / backward, attention core forward / backward in SIMT fp32)
+int gelu_f32_launch(const float* dy, const float* x, float* out, long n, cudaStream_t st);
+int attn_f32_launch(const float* qkv, float* o, float* lse, const float* d_o, float* dqkv, int B, int N, int H, int D,
+                    float scale, cudaStream_t st);
+
 // misc.cu
 int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S, int P, int Kp, cudaStream_t st);
 int assemble_launch(const __nv_bfloat16* pe, const float* cls, const float* pos, float* x, int B, int N, int C,

@@ -192,6 +192,34 @@ def attn_bwd(qkv, o, o_lo, lse, d_o, B, N, H, D, scale):
     return dqkv
 
 
+def gelu_f32(x, dy=None):
+    """fp32 mode: GELU(x) (dy None) or dy * GELU'(x), exact erf."""
+    st = _prep(x)
+    assert x.dtype == F32 and x.is_contiguous() and (dy is None or (dy.dtype == F32 and dy.is_contiguous()))
+    out = torch.empty_like(x)
+    L.check(L.lib().cara_gelu_f32(_p(dy), x.data_ptr(), out.data_ptr(), x.numel(), st), "cara_gelu_f32")
+    return out
+
+
+def attn_f32_fwd(qkv, B, N, H, D, scale, train=True):
+    """fp32 mode attention core: qkv fp32 [B,N,3,H,D] -> (o fp32 [B*N, H*D], lse [B,H,N] or None)."""
+    st = _prep(qkv)
+    assert qkv.dtype == F32 and qkv.is_contiguous() and qkv.numel() == B * N * 3 * H * D
+    o = torch.empty((B * N, H * D), device=qkv.device, dtype=F32)
+    lse = torch.empty((B, H, N), device=qkv.device, dtype=F32) if train else None
+    L.check(L.lib().cara_attn_f32(qkv.data_ptr(), o.data_ptr(), _p(lse), None, None, B, N, H, D, scale, st), "cara_attn_f32")
+    return o, lse
+
+
+def attn_f32_bwd(qkv, o, lse, d_o, B, N, H, D, scale):
+    st = _prep(qkv)
+    assert d_o.dtype == F32 and d_o.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    L.check(L.lib().cara_attn_f32(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(), dqkv.data_ptr(), B, N, H, D,
+                                  scale, st), "cara_attn_f32")
+    return dqkv
+
+
 def patchify(img, P, Kp):
     st = _prep(img)
     B, Cin, S, _ = img.shape

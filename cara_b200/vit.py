@@ -13,6 +13,7 @@ from functools import partial
 import torch
 import torch.nn as nn
 
+from . import fp32 as F32M
 from . import kernels as K
 from . import ops
 from ._lib import CaraLibraryError
@@ -85,6 +86,8 @@ def attn_forward(mod, x, staged):
     _require_cuda(x, "Attention.forward")
     if mod.attn_drop.p or mod.proj_drop.p:
         raise NotImplementedError("attn_drop/proj_drop > 0 are not part of the CaRA path (timm default 0)")
+    if F32M.is_fp32(mod):
+        return F32M.attn_forward(mod, x, staged)
     h, (B, N, C) = _as_act(x)
     H = mod.num_heads
     fq, fp = ops.FrozenLinear.of(mod.qkv), ops.FrozenLinear.of(mod.proj)
@@ -110,6 +113,8 @@ def mlp_forward(mod, x, staged):
         raise NotImplementedError("Mlp dropout > 0 is not part of the CaRA path (timm default 0)")
     if not isinstance(mod.act, nn.GELU) or getattr(mod.act, "approximate", "none") != "none":
         raise NotImplementedError("only the exact-erf nn.GELU of timm's Mlp is implemented")
+    if F32M.is_fp32(mod):
+        return F32M.mlp_forward(mod, x, staged)
     h, (B, N, C) = _as_act(x)
     f1, f2 = ops.FrozenLinear.of(mod.fc1), ops.FrozenLinear.of(mod.fc2)
     if staged is None:
@@ -141,7 +146,8 @@ class Block(nn.Module):
         _require_cuda(x, "Block.forward")
         B, N, C = x.shape
         xr = x.reshape(B * N, C).to(F32).contiguous()
-        h = ops.LayerNormFunction.apply(xr, self.norm1.weight, self.norm1.bias, self.norm1.eps, BF16)
+        h = ops.LayerNormFunction.apply(xr, self.norm1.weight, self.norm1.bias, self.norm1.eps,
+                                        F32 if F32M.is_fp32(self) else BF16)
         xr, pending = self.fused_step(xr, h, B, N)
         out = xr + pending[0].float() * (1.0 if pending[1] is None else pending[1].repeat_interleave(N)[:, None])
         return out.view(B, N, C).to(x.dtype)
@@ -183,6 +189,8 @@ class PatchEmbed(nn.Module):
     def forward(self, x):
         """[B,3,S,S] fp32 -> bf16 [B, num_patches, C] (im2col + tcgen05 GEMM)."""
         _require_cuda(x, "PatchEmbed.forward")
+        if F32M.is_fp32(self):
+            return F32M.patch_embed(self, x)
         wm, kp, bias = self._packed()
         patches = K.patchify(x.to(F32).contiguous(), self.patch_size[0], kp)
         return K.gemm_cp(patches, wm, bias=bias).view(x.shape[0], self.num_patches, -1)
@@ -250,12 +258,17 @@ class VisionTransformer(nn.Module):
         N = self.patch_embed.num_patches + 1
         with torch.no_grad():  # everything upstream of block 0 is frozen (vit_cp.py:176-182)
             pe = self.patch_embed(img)
-            x = K.assemble_tokens(pe.reshape(-1, C), self.cls_token.detach().reshape(C).float().contiguous(),
-                                  self.pos_embed.detach().reshape(N, C).float().contiguous(), B, N, C)
+            if F32M.is_fp32(self):   # token assembly is data movement + one add on the frozen path
+                x = (torch.cat([self.cls_token.detach().float().expand(B, -1, -1), pe], dim=1)
+                     + self.pos_embed.detach().float()).reshape(B * N, C).contiguous()
+            else:
+                x = K.assemble_tokens(pe.reshape(-1, C), self.cls_token.detach().reshape(C).float().contiguous(),
+                                      self.pos_embed.detach().reshape(N, C).float().contiguous(), B, N, C)
         pending = None
         for blk in self.blocks:
             if pending is None:
-                h = ops.LayerNormFunction.apply(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, BF16)
+                h = ops.LayerNormFunction.apply(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps,
+                                                F32 if F32M.is_fp32(self) else BF16)
             else:
                 x, h = ops.AddLayerNormFunction.apply(x, pending[0], pending[1], blk.norm1.weight, blk.norm1.bias,
                                                       blk.norm1.eps, N)

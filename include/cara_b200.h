@@ -104,6 +104,16 @@ CARA_API int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, con
  * kernels only write them for CTA 0); returns the number of values copied. */
 CARA_API int cara_debug_read(long long* out, int n);
 
+/* fp32 mode (north_star: logits rel-err <= 1e-4): plain SIMT fp32, no tensor cores.  Projections run on cara_sgemm,
+ * LayerNorm on cara_ln_fwd/bwd with act_fp32 = 1; these two add the exact-erf GELU (cara.py:84) and the attention core
+ * (cara.py:44-48) on fp32 [B,N,3,H,D] / [B,N,H,D] tensors (N <= 288, D <= 96; two [N, D+1] fp32 tiles of shared memory).
+ *   cara_gelu_f32: dy == NULL -> out = GELU(x);  else out = dy * GELU'(x).
+ *   cara_attn_f32: d_o == NULL -> forward (writes o and, if not NULL, lse = natural-log-sum-exp [B,H,N]);
+ *                  else backward (reads o, lse, d_o; writes dqkv). */
+CARA_API int cara_gelu_f32(const float* dy, const float* x, float* out, long n, void* stream);
+CARA_API int cara_attn_f32(const float* qkv, float* o, float* lse, const float* d_o, float* dqkv, int B, int N, int H,
+                           int D, float scale, void* stream);
+
 /* timm PatchEmbed (conv PxP stride P) as im2col: img fp32 [B,Cin,S,S] -> bf16 [B*(S/P)^2, Kp] (zero padded),
  * then cara_gemm_cp against the flattened conv weight, then token assembly with cls/pos into the fp32
  * residual stream x [B,N,C]. */

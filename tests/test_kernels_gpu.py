@@ -261,3 +261,27 @@ def test_merge_adamw_sgemm(K):
     bias = torch.randn(100, device="cuda", generator=g)
     assert rel(K.sgemm(a, b.t(), bias=bias), a @ b.t() + bias) < 1e-5
     assert rel(K.sgemm(a.t(), a), a.t() @ a) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,H,D", [(2, 197, 3, 64), (1, 257, 2, 80), (2, 33, 2, 64)])
+def test_fp32_mode_attention_and_gelu(K, B, N, H, D):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(B, N, 3, H, D, device="cuda", generator=g)
+    scale = D ** -0.5
+    o, lse = K.attn_f32_fwd(qkv.view(-1), B, N, H, D, scale)
+    q, k, v = [t.double().requires_grad_(True) for t in qkv.permute(2, 0, 3, 1, 4)]
+    att = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+    oref = (att @ v).transpose(1, 2).reshape(B * N, H * D)
+    assert rel(o, oref.detach()) < 2e-6
+    d_o = torch.randn(B * N, H * D, device="cuda", generator=g)
+    oref.backward(d_o.double())
+    dqkv = K.attn_f32_bwd(qkv.view(-1), o, lse, d_o, B, N, H, D, scale).view(B, N, 3, H, D)
+    dref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4)
+    assert rel(dqkv, dref) < 5e-6
+    u = torch.randn(1000, 37, device="cuda", generator=g) * 2
+    ud = u.double().requires_grad_(True)
+    yd = torch.nn.functional.gelu(ud)
+    assert rel(K.gelu_f32(u), yd.detach()) < 1e-6
+    dy = torch.randn_like(u)
+    yd.backward(dy.double())
+    assert rel(K.gelu_f32(u, dy=dy), ud.grad) < 2e-6

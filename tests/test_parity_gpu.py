@@ -190,3 +190,40 @@ def test_fused_adamw_step_matches_oracle_update():
             want, _, _ = O.adamw_update(before[n], gr, torch.zeros_like(gr), torch.zeros_like(gr), 1)
             assert rel(p.detach().cpu(), want) < 1e-6, n
     assert abs(float(loss) - float(O.loss_and_grads(st, g, x, y, 1.0)[1])) < 3e-2
+
+
+def test_fp32_mode_matches_reference_golden():
+    """north_star fp32 bar: logits rel-err <= 1e-4 against the reference's own fp32 outputs (full ViT-B/16, rank 16);
+    gradients of all 14 trainable tensors to 1e-3 (SIMT fp32 kernels end to end, no tensor cores)."""
+    from cara_b200.fp32 import set_precision
+    z = np.load(os.path.join(G, "ref_vitb_d12_r16_fp32.npz"))
+    g = O.Geometry(depth=12, rank=16, num_classes=100)
+    vit, _ = build(g, float(z["scale"]))
+    set_precision(vit, "fp32")
+    vit.eval()
+    x, y = O.synthetic_batch(g, int(z["batch"]))
+    logits, loss, grads = run_step(vit, x, y)
+    e = rel(logits, z["logits"])
+    print("fp32 mode vs reference golden: logits rel %.3e" % e)
+    assert e <= 1e-4, e
+    assert abs(loss - float(z["loss"])) <= 1e-4 * max(1.0, abs(float(z["loss"])))
+    for k in z.files:
+        if k.startswith("grad."):
+            assert rel(grads[k[5:]], z[k]) <= 1e-3, (k, rel(grads[k[5:]], z[k]))
+            assert cos(grads[k[5:]], z[k]) >= 0.99999, k
+
+
+def test_fp32_mode_vs_fp64_oracle_reduced_depth():
+    """fp32 mode on a depth-2 model with a large adapter scale, against the oracle evaluated in fp64."""
+    from cara_b200.fp32 import set_precision
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    vit, st = build(g, 2.5)
+    set_precision(vit, "fp32")
+    vit.eval()
+    x, y = O.synthetic_batch(g, 3)
+    logits, loss, grads = run_step(vit, x, y)
+    st64 = {k: (v.double() if v.is_floating_point() else v) for k, v in st.items()}
+    o_logits, o_loss, o_grads = O.loss_and_grads(st64, g, x.double(), y, 2.5)
+    assert rel(logits, o_logits) <= 1e-4
+    for k in o_grads:
+        assert rel(grads[k], o_grads[k]) <= 1e-3, (k, rel(grads[k], o_grads[k]))
