@@ -55,12 +55,20 @@ def staged(model):
     C = P["CP_A2"].shape[0]
     f = {n: p.float() for n, p in P.items()}
     La, Lm = len(attn), len(mlp)
-    ai = torch.tensor([int(m.attn_idx) for m in attn], device=dev)
-    pi = torch.tensor([int(m.idx) for m in attn], device=dev)
-    mi = torch.tensor([int(m.idx) for m in mlp], device=dev)
-    s_a = torch.tensor([float(m.s) for m in attn], device=dev, dtype=F32).view(La, 1, 1)
-    s_m = torch.tensor([float(m.s) for m in mlp], device=dev, dtype=F32).view(Lm, 1, 1)
-    r3, r4 = torch.arange(3, device=dev), torch.arange(4, device=dev)
+    # index / scale tensors: built once per (indices, scales) -- a host list -> device copy is a synchronous
+    # transfer, which must not happen inside a CUDA-graph capture of the step
+    ikey = (key[3], key[5], key[6], str(dev))
+    icache = model.__dict__.get("_cara_stage_idx")
+    if icache is None or icache[0] != ikey:
+        icache = (ikey,
+                  torch.tensor([int(m.attn_idx) for m in attn], device=dev),
+                  torch.tensor([int(m.idx) for m in attn], device=dev),
+                  torch.tensor([int(m.idx) for m in mlp], device=dev),
+                  torch.tensor([float(m.s) for m in attn], device=dev, dtype=F32).view(La, 1, 1),
+                  torch.tensor([float(m.s) for m in mlp], device=dev, dtype=F32).view(Lm, 1, 1),
+                  torch.arange(3, device=dev), torch.arange(4, device=dev))
+        model.__dict__["_cara_stage_idx"] = icache
+    _, ai, pi, mi, s_a, s_m, r3, r4 = icache
 
     kr_attn = (f["CP_A3"][:, None, :] * f["CP_A4"][None, :, :]).reshape(C, R)            # B of qkv
     cs_qkv = s_a * (f["CP_R1"] * f["CP_A1"][ai[:, None] + r3])                            # [La,3,R]

@@ -114,3 +114,51 @@ def train_step(model, opt, x, y, world_size=1):
     allreduce_grads(opt.flat, world_size)
     opt.step(grad_scale=1.0 / world_size)
     return loss
+
+
+class GraphedStep:
+    """``train_step`` with zero_grad + forward + cross-entropy + backward replayed from ONE CUDA graph.
+
+    A step is ~1,800 kernel launches whose host-side enqueue (autograd + ctypes) takes longer than half of the
+    device time; the batch shape of vit_cp.py's loop is fixed (vtab.py:84-88, drop_last), so the whole launch
+    sequence is captured once and replayed.  The gradient all-reduce and the fused AdamW kernel stay outside the
+    graph (two launches; the optimizer's step count and learning rate are host scalars that change every step).
+    Inputs are copied into the graph's static buffers on the launching stream before each replay.
+    """
+
+    def __init__(self, model, opt, x, y, world_size=1, warmup=3):
+        self.model, self.opt, self.world_size = model, opt, world_size
+        self.x = torch.empty_like(x)
+        self.y = torch.empty_like(y)
+        self.x.copy_(x)
+        self.y.copy_(y)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # eager runs: caches, lazily configured kernels, allocator warm-up
+                self._fwd_bwd()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        before = K.launch_count
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+        self.launches_per_replay = K.launch_count - before   # cara_* kernels inside the graph (bench: gpu_launches)
+
+    def _fwd_bwd(self):
+        self.opt.zero_grad()
+        out = self.model(self.x)
+        loss = torch.nn.functional.cross_entropy(out, self.y)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, x, y):
+        if x.shape != self.x.shape or y.shape != self.y.shape:
+            raise ValueError("GraphedStep was captured for batch shape %s" % (tuple(self.x.shape),))
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        K.launch_count += self.launches_per_replay
+        allreduce_grads(self.opt.flat, self.world_size)
+        self.opt.step(grad_scale=1.0 / self.world_size)
+        return self.loss
