@@ -57,5 +57,4 @@ if __name__ == "__main__":
     if L.lib().cara_debug_read(buf, 64) and buf[0]:
         v = list(buf)
         base = v[0]
-        print("control: in->%s" % [(i, v[i] - base) for i in (1, 2, 3, 9, 10, 11, 20) if v[i]])
-        print("compute: %s" % [(i, v[i] - base) for i in range(32, 64) if v[i]])
+        print("stamps (cycles after stamp 0): %s" % [(i, v[i] - base) for i in range(1, 64) if v[i]])
