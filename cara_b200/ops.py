@@ -62,6 +62,41 @@ class AdapterOperands:
         return AdapterOperands(a_ext, a_t2, b_ext, b_t2, cs_pad, R)
 
 
+class GradSink:
+    """One zero-filled fp32 buffer per root forward that every projection's backward kernels accumulate their
+    factor gradients into (the kernels add atomically anyway).  Without it each of the 4L projections hands
+    autograd four fresh tensors, and the engine spends ~350 tiny fill / add launches per step summing them into
+    the shared ``CP_*`` terms.  Per projection kind k (0 qkv, 1 proj, 2 fc1, 3 fc2):
+    ``dA[k]`` [K,Rp] (fc2: [L,4C,Rp], its in-side factor is per layer), ``dB[k]`` [N/S,Rp], ``dcs[k]`` [L,S,Rp],
+    ``dbias[k]`` [L,N] (None for qkv).  The gradients are returned to autograd once per kind, by the last
+    backward of that kind (``release``); the others return None."""
+
+    def __init__(self, L_, C, Rp, device):
+        shapes = {"dA0": (C, Rp), "dB0": (C, Rp), "dcs0": (L_, 3, Rp),
+                  "dA1": (C, Rp), "dB1": (C, Rp), "dcs1": (L_, 1, Rp), "db1": (L_, C),
+                  "dA2": (C, Rp), "dB2": (C, Rp), "dcs2": (L_, 4, Rp), "db2": (L_, 4 * C),
+                  "dA3": (L_, 4 * C, Rp), "dB3": (C, Rp), "dcs3": (L_, 1, Rp), "db3": (L_, C)}
+        sizes = [int(torch.Size(v).numel()) for v in shapes.values()]
+        self.buf = torch.zeros(sum(sizes), device=device, dtype=F32)
+        self.t = {k: v.view(shapes[k]) for k, v in zip(shapes, torch.split(self.buf, sizes))}
+        self.pending = [0, 0, 0, 0]
+
+    def views(self, kind, layer, need_bias):
+        dA = self.t["dA%d" % kind]
+        if kind == 3:
+            dA = dA[layer]
+        db = self.t["db%d" % kind][layer] if (need_bias and kind > 0) else None
+        return dA, self.t["dcs%d" % kind][layer], self.t["dB%d" % kind], db
+
+    def release(self, kind, R, need_bias):
+        """-> (dA, dcs, dB, dbias) for autograd if this was the last pending backward of ``kind``, else Nones."""
+        self.pending[kind] -= 1
+        if self.pending[kind] > 0:
+            return None, None, None, None
+        db = self.t["db%d" % kind] if (need_bias and kind > 0) else None
+        return self.t["dA%d" % kind][..., :R], self.t["dcs%d" % kind][..., :R], self.t["dB%d" % kind][..., :R], db
+
+
 def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True):
     T = U = None
     if ops is not None:
@@ -72,8 +107,9 @@ def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True):
     return y, T, U
 
 
-def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None):
-    """Returns (dx, dA, dcs, dB, dbias)."""
+def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink=None):
+    """Returns (dx, dA, dcs, dB, dbias).  ``sink`` = (GradSink, kind, layer): accumulate the factor gradients
+    there and hand them to autograd once per projection kind (see GradSink)."""
     epi = L.EPI_DGELU if dgelu_aux is not None else L.EPI_NONE
     if ops is None:
         dx = K.gemm_cp(G, fz.wt, epi=epi, aux=dgelu_aux) if need_dx else None
@@ -81,18 +117,23 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None):
     R, Rp, S = ops.rank, ops.rp, ops.slices
     Kin, N = x.shape[1], G.shape[1]
     w = N // S
-    # one zero fill for every atomically accumulated output of this projection's backward
-    sizes = (S * Rp, Kin * Rp, w * Rp, N if need_bias else 0)
-    z = torch.zeros(sum(sizes), device=G.device, dtype=F32)
-    zs = torch.split(z, sizes)
-    dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
-    colsum = zs[3] if need_bias else None
+    if sink is not None:
+        dA, dcs, dB, colsum = sink[0].views(sink[1], sink[2], need_bias)
+    else:
+        # one zero fill for every atomically accumulated output of this projection's backward
+        sizes = (S * Rp, Kin * Rp, w * Rp, N if need_bias else 0)
+        z = torch.zeros(sum(sizes), device=G.device, dtype=F32)
+        zs = torch.split(z, sizes)
+        dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
+        colsum = zs[3] if need_bias else None
     dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
     dx = None
     if need_dx:
         dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux)
     K.adapter_cols(x, dT, 1, Rp, out=dA)
     K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
+    if sink is not None:
+        return (dx,) + sink[0].release(sink[1], R, need_bias)
     return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum
 
 
@@ -100,9 +141,15 @@ class CPLinearFunction(torch.autograd.Function):
     """One CP-adapted frozen projection (qkv: cara.py:25-42, proj: cara.py:50-58)."""
 
     @staticmethod
-    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops):
-        y, T, U = _cp_linear_fwd(x, fz, bias_eff if bias_eff is not None else fz.bias, ops)
-        ctx.fz, ctx.ops = fz, ops
+    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops, sink=None):
+        """Without ``sink``: A [K,R], cs [S,R], Bf [N/S,R], bias_eff [N] are this layer's terms.  With ``sink`` =
+        (GradSink, kind, layer): cs [L,S,R] and bias_eff [L,N] (and A [L,4C,R] for fc2) are the stacked terms of
+        all layers -- autograd sees one gradient per kind instead of one per layer."""
+        bias = bias_eff if (bias_eff is None or sink is None) else bias_eff[sink[2]]
+        y, T, U = _cp_linear_fwd(x, fz, bias if bias is not None else fz.bias, ops)
+        if sink is not None and any(ctx.needs_input_grad):
+            sink[0].pending[sink[1]] += 1
+        ctx.fz, ctx.ops, ctx.sink = fz, ops, sink
         ctx.save_for_backward(x, T, U)
         return y
 
@@ -110,8 +157,8 @@ class CPLinearFunction(torch.autograd.Function):
     def backward(ctx, G):
         x, T, U = ctx.saved_tensors
         ni = ctx.needs_input_grad
-        dx, dA, dcs, dB, dbias = _cp_linear_bwd(G.contiguous(), x, ctx.fz, ctx.ops, T, U, ni[0], ni[4])
-        return dx, dA, dcs, dB, dbias, None, None
+        dx, dA, dcs, dB, dbias = _cp_linear_bwd(G.contiguous(), x, ctx.fz, ctx.ops, T, U, ni[0], ni[4], sink=ctx.sink)
+        return dx, dA, dcs, dB, dbias, None, None, None
 
 
 class CPMlpFunction(torch.autograd.Function):
@@ -119,12 +166,19 @@ class CPMlpFunction(torch.autograd.Function):
     GELU is applied in the fc1 GEMM epilogue and its derivative in the fc2 dX GEMM epilogue."""
 
     @staticmethod
-    def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, fz1, ops1, fz2, ops2):
+    def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, fz1, ops1, fz2, ops2, sink1=None, sink2=None):
         train = any(ctx.needs_input_grad)
+        if sink1 is not None:                 # stacked terms of all layers (see CPLinearFunction.forward)
+            bias1 = None if bias1 is None else bias1[sink1[2]]
+            bias2 = None if bias2 is None else bias2[sink2[2]]
+            if train:
+                sink1[0].pending[sink1[1]] += 1
+                sink2[0].pending[sink2[1]] += 1
         (u, g), T1, U1 = _cp_linear_fwd(x, fz1, bias1 if bias1 is not None else fz1.bias, ops1, epi=L.EPI_GELU,
                                         want_pre=train)
         y, T2, U2 = _cp_linear_fwd(g, fz2, bias2 if bias2 is not None else fz2.bias, ops2)
         ctx.fz1, ctx.ops1, ctx.fz2, ctx.ops2 = fz1, ops1, fz2, ops2
+        ctx.sink1, ctx.sink2 = sink1, sink2
         ctx.save_for_backward(x, u, g, T1, U1, T2, U2)
         return y
 
@@ -133,9 +187,9 @@ class CPMlpFunction(torch.autograd.Function):
         x, u, g, T1, U1, T2, U2 = ctx.saved_tensors
         ni = ctx.needs_input_grad
         du, dA2, dcs2, dB2, db2 = _cp_linear_bwd(G.contiguous(), g, ctx.fz2, ctx.ops2, T2, U2, True, ni[8],
-                                                 dgelu_aux=u)
-        dx, dA1, dcs1, dB1, db1 = _cp_linear_bwd(du, x, ctx.fz1, ctx.ops1, T1, U1, ni[0], ni[4])
-        return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None
+                                                 dgelu_aux=u, sink=ctx.sink2)
+        dx, dA1, dcs1, dB1, db1 = _cp_linear_bwd(du, x, ctx.fz1, ctx.ops1, T1, U1, ni[0], ni[4], sink=ctx.sink1)
+        return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None, None, None
 
 
 class AttnCoreFunction(torch.autograd.Function):

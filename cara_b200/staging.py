@@ -11,7 +11,7 @@ follow the reference's own indices: ``CP_A1[attn_idx : attn_idx+3]`` (cara.py:26
 import torch
 
 from . import kernels as K
-from .ops import AdapterOperands
+from .ops import AdapterOperands, GradSink
 
 BF16, F32 = torch.bfloat16, torch.float32
 CP_NAMES = ("CP_A1", "CP_A2", "CP_A3", "CP_A4", "CP_P1", "CP_P2", "CP_P3", "CP_R1", "CP_R2",
@@ -19,10 +19,20 @@ CP_NAMES = ("CP_A1", "CP_A2", "CP_A3", "CP_A4", "CP_P1", "CP_P2", "CP_P3", "CP_R
 
 
 class Terms:
-    __slots__ = ("A", "cs", "B", "bias", "ops")
+    """One projection's terms.  ``A cs B bias`` are this layer's tensors (fp32 parity mode, un-sunk path);
+    ``stacked`` = (A or A[L,..], cs [L,S,R], B, bias [L,N] or None) are the all-layer tensors the bf16 path hands to
+    autograd together with ``sink`` = (ops.GradSink, kind, layer) when gradients are on."""
+    __slots__ = ("A", "cs", "B", "bias", "ops", "stacked", "sink")
 
-    def __init__(self, A, cs, B, bias, ops):
+    def __init__(self, A, cs, B, bias, ops, stacked=None, sink=None):
         self.A, self.cs, self.B, self.bias, self.ops = A, cs, B, bias, ops
+        self.stacked, self.sink = stacked, sink
+
+    def autograd_args(self):
+        """(A, cs, B, bias, sink) for ops.CPLinearFunction / CPMlpFunction."""
+        if self.sink is not None:
+            return self.stacked + (self.sink,)
+        return self.A, self.cs, self.B, self.bias, None
 
 
 def _modules(model):
@@ -89,16 +99,23 @@ def staged(model):
         pad = lambda t: torch.nn.functional.pad(t.detach(), (0, Rp - R)).contiguous()  # noqa: E731
         csq, csp, cs1, cs2 = pad(cs_qkv), pad(cs_proj), pad(cs_fc1), pad(cs_fc2)
 
+    # gradients on: every projection's backward accumulates into one zero-filled sink (ops.GradSink)
+    sink = GradSink(max(La, Lm), C, Rp, dev) if (grad_on and La == Lm) else None
+    sk = (lambda kind, i: (sink, kind, i)) if sink is not None else (lambda kind, i: None)
     amap, mmap = {}, {}
     for i, m in enumerate(attn):
-        qkv = Terms(f["CP_A2"], cs_qkv[i], kr_attn, None, AdapterOperands(a2_pad, a2_t, kr_pad, kr_t, csq[i], R))
+        qkv = Terms(f["CP_A2"], cs_qkv[i], kr_attn, None, AdapterOperands(a2_pad, a2_t, kr_pad, kr_t, csq[i], R),
+                    (f["CP_A2"], cs_qkv, kr_attn, None), sk(0, i))
         proj = Terms(f["CP_P3"], cs_proj[i], f["CP_P2"], b_proj[i],
-                     AdapterOperands(p3_pad, p3_t, p2_pad, p2_t, csp[i], R))
+                     AdapterOperands(p3_pad, p3_t, p2_pad, p2_t, csp[i], R),
+                     (f["CP_P3"], cs_proj, f["CP_P2"], b_proj), sk(1, i))
         amap[id(m)] = (qkv, proj)
     for i, m in enumerate(mlp):
-        fc1 = Terms(f["CP_P3"], cs_fc1[i], f["CP_P2"], b_fc1[i], AdapterOperands(p3_pad, p3_t, p2_pad, p2_t, cs1[i], R))
+        fc1 = Terms(f["CP_P3"], cs_fc1[i], f["CP_P2"], b_fc1[i], AdapterOperands(p3_pad, p3_t, p2_pad, p2_t, cs1[i], R),
+                    (f["CP_P3"], cs_fc1, f["CP_P2"], b_fc1), sk(2, i))
         fc2 = Terms(a_fc2[i], cs_fc2[i], f["CP_P3"], b_fc2[i],
-                    AdapterOperands(afc2_pad[i], afc2_t[i], p3_pad, p3_t, cs2[i], R))
+                    AdapterOperands(afc2_pad[i], afc2_t[i], p3_pad, p3_t, cs2[i], R),
+                    (a_fc2, cs_fc2, f["CP_P3"], b_fc2), sk(3, i))
         mmap[id(m)] = (fc1, fc2)
     model.__dict__["_cara_stage"] = (key, amap, mmap, token)
     return amap, mmap

@@ -94,14 +94,14 @@ def attn_forward(mod, x, staged):
     if staged is None:
         qkv = ops.CPLinearFunction.apply(h, None, None, None, None, fq, None)
     else:
-        t = staged[0]
-        qkv = ops.CPLinearFunction.apply(h, t.A, t.cs, t.B, None, fq, t.ops)
+        A, cs, Bf, _, sink = staged[0].autograd_args()
+        qkv = ops.CPLinearFunction.apply(h, A, cs, Bf, None, fq, staged[0].ops, sink)
     o = ops.AttnCoreFunction.apply(qkv, B, N, H, C // H, float(mod.scale))
     if staged is None:
         y = ops.CPLinearFunction.apply(o, None, None, None, None, fp, None)
     else:
-        t = staged[1]
-        y = ops.CPLinearFunction.apply(o, t.A, t.cs, t.B, t.bias, fp, t.ops)
+        A, cs, Bf, bias, sink = staged[1].autograd_args()
+        y = ops.CPLinearFunction.apply(o, A, cs, Bf, bias, fp, staged[1].ops, sink)
     y = y.view(B, N, C)
     return y if x.dtype == BF16 else y.to(x.dtype)
 
@@ -121,7 +121,9 @@ def mlp_forward(mod, x, staged):
         y = ops.CPMlpFunction.apply(h, None, None, None, None, None, None, None, None, f1, None, f2, None)
     else:
         u, d = staged
-        y = ops.CPMlpFunction.apply(h, u.A, u.cs, u.B, u.bias, d.A, d.cs, d.B, d.bias, f1, u.ops, f2, d.ops)
+        a1, c1, b1, bi1, s1 = u.autograd_args()
+        a2, c2, b2, bi2, s2 = d.autograd_args()
+        y = ops.CPMlpFunction.apply(h, a1, c1, b1, bi1, a2, c2, b2, bi2, f1, u.ops, f2, d.ops, s1, s2)
     y = y.view(B, N, -1)
     return y if x.dtype == BF16 else y.to(x.dtype)
 

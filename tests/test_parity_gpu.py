@@ -108,10 +108,14 @@ def test_halves_match_reference_golden():
 
 
 def test_train_mode_droppath_replay():
-    """Stochastic depth: replay the per-sample multipliers the CUDA path drew through the oracle."""
-    g = O.Geometry(depth=3, rank=16, num_classes=10)
-    vit, st = build(g, 1.0, drop_path=0.5)
+    """Stochastic depth: replay the per-sample multipliers the CUDA path drew through the oracle.  Full depth
+    with a raised rate (0.3 at the last block; the shipped rate 0.1 rarely drops anything at batch 4), seeded
+    draws, the strict 1e-2 bar."""
+    g = O.Geometry(depth=12, rank=16, num_classes=10)
+    vit, st = build(g, 1.0, drop_path=0.3)
     vit.train()
+    torch.manual_seed(7)
+    torch.cuda.manual_seed_all(7)
     import warnings
     drawn = []
     from cara_b200 import vit as V
@@ -137,8 +141,9 @@ def test_train_mode_droppath_replay():
                 rs = next(it)
                 if rs is not None:
                     keep[l, j] = rs
+    assert int((keep == 0).sum()) >= 4, "the seeded draw must actually drop some residual branches"
     o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, 1.0, keep=keep)
-    check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, "droppath", logits_tol=1.5e-2)  # 3 blocks
+    check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, "droppath")
 
 
 def test_reference_forward_shape():
