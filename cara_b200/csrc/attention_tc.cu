@@ -175,22 +175,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a
       if (warp_live && row < N) {
         const float inv = 1.0f / l;
         const long off = (static_cast<long>(b) * N + row) * C + h * TC_D;
-        uint4* po = reinterpret_cast<uint4*>(a.o + off);
-        uint4* pl = a.o_lo != nullptr ? reinterpret_cast<uint4*>(a.o_lo + off) : nullptr;
+        __nv_bfloat16* po = a.o + off;
+        __nv_bfloat16* pl = a.o_lo != nullptr ? a.o_lo + off : nullptr;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v[8];
-          uint32_t hi[4], lo[4];
+        for (int j = 0; j < 4; ++j) {
+          float v[16];
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * j + e]) * inv;
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(o[16 * j + e]) * inv;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 8; ++e) {
             hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
             const float2 hf = unpack_bf16(hi[e]);
             lo[e] = pack_bf16(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
           }
-          po[j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (pl != nullptr) pl[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          st_global_v8(po + 16 * j, hi);
+          if (pl != nullptr) st_global_v8(pl + 16 * j, lo);
         }
         if (a.lse != nullptr) a.lse[(static_cast<long>(b) * a.H + h) * N + row] = mx * sl2 + log2f(l);
       }
@@ -262,19 +262,22 @@ __device__ __forceinline__ void named_bar_sync_256() { asm volatile("bar.sync 1,
 
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
-                   const AttnArgs a, const int npad) {
+                   const AttnArgs a, const int npad, const int qk_pairs) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tile0 = (raw + 1023u) & ~1023u;
   const uint32_t tile_bytes = static_cast<uint32_t>(npad) * 128u;
-  const uint32_t sQ = tile0, sK = sQ + tile_bytes, sV = sK + tile_bytes, sDO = sV + tile_bytes;
-  // the second key tile's A operands read 128 rows from row 128 of sK / sV whatever npad is: what lies behind
-  // them (sV, sDO, then the dS^T tile) is allocated and always holds finite bf16 data
+  // Input tiles: qk_pairs (1 or 2) x {Q, K}, then V, dO.  With two Q/K pairs (whenever they fit: N <= 208) the next
+  // head's Q and K land while this head is being computed; V / dO are reloaded in place as soon as the last MMA
+  // that reads them has retired (V: last dP^T, dO: last dV), so no load is exposed between heads.
+  // The second key tile's A operands read 128 rows from row 128 of K / V whatever npad is: what lies behind them
+  // (the next tile, then the dS^T tile) is allocated and always holds finite bf16 data (possibly mid-reload).
+  const uint32_t sV = tile0 + 2u * static_cast<uint32_t>(qk_pairs) * tile_bytes, sDO = sV + tile_bytes;
   const uint32_t sDS = sDO + tile_bytes;
   const uint32_t stats = sDS + TCB_DS_BYTES;                 // nlse[256], delta[256] (fp32)
   const uint32_t bars = stats + 2048u;
-  const uint32_t bar_in = bars, bar_sdp = bars + 8, bar_pds = bars + 16, bar_kv = bars + 24, bar_out = bars + 32,
-                 bar_rd = bars + 40, tmem_slot = bars + 48;
+  const uint32_t bar_sdp = bars + 8, bar_pds = bars + 16, bar_kv = bars + 24, bar_out = bars + 32,
+                 bar_rd = bars + 40, tmem_slot = bars + 48, bar_qk0 = bars + 56, bar_v = bars + 72, bar_do = bars + 80;
   float* s_nlse = reinterpret_cast<float*>(smem_raw + (stats - raw));
   float* s_delta = s_nlse + 256;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -290,7 +293,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     if (lane == 0) {
       tma_prefetch_desc(&map_qkv);
       tma_prefetch_desc(&map_do);
-      mbar_init(bar_in, 1);
+      mbar_init(bar_qk0, 1);
+      mbar_init(bar_qk0 + 8, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_do, 1);
       mbar_init(bar_sdp, 1);
       mbar_init(bar_pds, 256);
       mbar_init(bar_kv, 1);
@@ -313,23 +319,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
   if (warp == 8) {
     if (lane == 0) {
-      auto issue_loads = [&](int head) {
-        const int b = head / a.H, h = head % a.H;
-        const int row0 = b * N;
-        mbar_expect_tx(bar_in, 4u * tile_bytes);
-        tma_load_2d(sK, &map_qkv, bar_in, C + h * TC_D, row0);
-        tma_load_2d(sQ, &map_qkv, bar_in, h * TC_D, row0);
-        tma_load_2d(sV, &map_qkv, bar_in, 2 * C + h * TC_D, row0);
-        tma_load_2d(sDO, &map_do, bar_in, h * TC_D, row0);
+      auto head_coords = [&](int head, int& row0, int& col) { row0 = (head / a.H) * N; col = (head % a.H) * TC_D; };
+      auto load_qk = [&](int head, uint32_t pair) {
+        int row0, col;
+        head_coords(head, row0, col);
+        const uint32_t q = tile0 + 2u * pair * tile_bytes, bar = bar_qk0 + 8u * pair;
+        mbar_expect_tx(bar, 2u * tile_bytes);
+        tma_load_2d(q + tile_bytes, &map_qkv, bar, C + col, row0);
+        tma_load_2d(q, &map_qkv, bar, col, row0);
+      };
+      auto load_v = [&](int head) {
+        int row0, col;
+        head_coords(head, row0, col);
+        mbar_expect_tx(bar_v, tile_bytes);
+        tma_load_2d(sV, &map_qkv, bar_v, 2 * C + col, row0);
+      };
+      auto load_do = [&](int head) {
+        int row0, col;
+        head_coords(head, row0, col);
+        mbar_expect_tx(bar_do, tile_bytes);
+        tma_load_2d(sDO, &map_do, bar_do, col, row0);
       };
       const uint32_t idesc_s = umma_idesc_bf16_major(128, npad, 0, 0);
       constexpr uint32_t idesc_dv = umma_idesc_bf16_major(128, TC_D, 0, 1);   // A from TMEM (K-major), B MN-major
       constexpr uint32_t idesc_dk = umma_idesc_bf16_major(128, TC_D, 0, 1);   // A K-major smem, B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16_major(128, TC_D, 1, 1);   // A MN-major smem, B MN-major
       uint32_t it = 0, n = 0;
-      if (static_cast<int>(blockIdx.x) < heads) issue_loads(blockIdx.x);
+      if (static_cast<int>(blockIdx.x) < heads) {
+        load_qk(blockIdx.x, 0);
+        load_v(blockIdx.x);
+        load_do(blockIdx.x);
+      }
       for (int head = blockIdx.x; head < heads; head += gridDim.x, ++it) {
-        mbar_wait(bar_in, it & 1u);
+        const int next = head + static_cast<int>(gridDim.x);
+        const uint32_t pair = qk_pairs == 2 ? (it & 1u) : 0u;
+        const uint32_t sQ = tile0 + 2u * pair * tile_bytes, sK = sQ + tile_bytes;
+        // the other Q/K pair was last read by the previous head, whose MMAs have all retired (wait at its end)
+        if (qk_pairs == 2 && next < heads) load_qk(next, pair ^ 1u);
+        mbar_wait(bar_qk0 + 8u * pair, (qk_pairs == 2 ? (it >> 1) : it) & 1u);
         if (it == 1) DBG_STAMP(0);
         for (int t = 0; t < nt; ++t, ++n) {
           if (n > 0) mbar_wait(bar_rd, (n - 1u) & 1u);         // previous outputs have been read out of TMEM
@@ -337,14 +364,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           if (it == 1) DBG_STAMP(1 + 8 * t);
           {
             const uint64_t dk = umma_desc_sw128(sK + static_cast<uint32_t>(t) * 16384u), dq = umma_desc_sw128(sQ);
-            const uint64_t dv = umma_desc_sw128(sV + static_cast<uint32_t>(t) * 16384u), dd = umma_desc_sw128(sDO);
 #pragma unroll
             for (int k = 0; k < TC_D / 16; ++k) umma_bf16(tmem_base, dk + 2u * k, dq + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+            if (t == 0) {
+              mbar_wait(bar_v, it & 1u);
+              mbar_wait(bar_do, it & 1u);
+              tc_fence_after();
+            }
+            const uint64_t dv = umma_desc_sw128(sV + static_cast<uint32_t>(t) * 16384u), dd = umma_desc_sw128(sDO);
 #pragma unroll
             for (int k = 0; k < TC_D / 16; ++k)
               umma_bf16(tmem_base + TCB_DP_COL, dv + 2u * k, dd + 2u * k, idesc_s, k != 0 ? 1u : 0u);
           }
           umma_commit(bar_sdp);
+          if (t == nt - 1 && next < heads) {                    // V is dead once the last dP^T has retired
+            mbar_wait(bar_sdp, n & 1u);
+            load_v(next);
+          }
           mbar_wait(bar_pds, n & 1u);                           // P^T is in TMEM, dS^T in shared memory
           tc_fence_after();
           if (it == 1) DBG_STAMP(2 + 8 * t);
@@ -373,12 +409,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             }
           }
           umma_commit(bar_out);
+          if (t == nt - 1 && next < heads) {                    // dO is dead once the last dV has retired
+            mbar_wait(bar_kv, n & 1u);
+            load_do(next);
+          }
           if (it == 1) DBG_STAMP(3 + 8 * t);
         }
-        // every MMA that reads this head's tiles has been issued; once they retire the next head may land
+        // every MMA that reads this head's Q / K has been issued; once they retire that pair may be refilled
         mbar_wait(bar_out, (n - 1u) & 1u);
         if (it == 1) DBG_STAMP(20);
-        if (head + static_cast<int>(gridDim.x) < heads) issue_loads(head + gridDim.x);
+        if (qk_pairs == 1 && next < heads) load_qk(next, 0);
       }
     }
   } else {
@@ -466,7 +506,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (warp_live) {
           const uint32_t col = half == 0 ? TCB_DK_COL : TCB_DV_COL;
           const float sc = half == 0 ? a.scale : 1.0f;
-          uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<long>(key) * 3 * C + (half == 0 ? C : 2 * C));
+          __nv_bfloat16* dst = gbase + static_cast<long>(key) * 3 * C + (half == 0 ? C : 2 * C);
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
             uint32_t r[32];
@@ -474,12 +514,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tmem_ld_wait();
             if (key_ok) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                dst[4 * part + j] =
-                    make_uint4(pack_bf16(__uint_as_float(r[8 * j + 0]) * sc, __uint_as_float(r[8 * j + 1]) * sc),
-                               pack_bf16(__uint_as_float(r[8 * j + 2]) * sc, __uint_as_float(r[8 * j + 3]) * sc),
-                               pack_bf16(__uint_as_float(r[8 * j + 4]) * sc, __uint_as_float(r[8 * j + 5]) * sc),
-                               pack_bf16(__uint_as_float(r[8 * j + 6]) * sc, __uint_as_float(r[8 * j + 7]) * sc));
+              for (int j = 0; j < 2; ++j) {
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  w[e] = pack_bf16(__uint_as_float(r[16 * j + 2 * e]) * sc, __uint_as_float(r[16 * j + 2 * e + 1]) * sc);
+                st_global_v8(dst + 32 * part + 16 * j, w);
               }
             }
           }
@@ -505,13 +545,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       // ---- dQ rows of query tile `half`
       const int qrow = half * 128 + key_local;
       if (half < nt && qrow < N) {
-        uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<long>(qrow) * 3 * C);
+        __nv_bfloat16* dst = gbase + static_cast<long>(qrow) * 3 * C;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          dst[j] = make_uint4(pack_bf16(dq[8 * j + 0] * a.scale, dq[8 * j + 1] * a.scale),
-                              pack_bf16(dq[8 * j + 2] * a.scale, dq[8 * j + 3] * a.scale),
-                              pack_bf16(dq[8 * j + 4] * a.scale, dq[8 * j + 5] * a.scale),
-                              pack_bf16(dq[8 * j + 6] * a.scale, dq[8 * j + 7] * a.scale));
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = pack_bf16(dq[16 * j + 2 * e] * a.scale, dq[16 * j + 2 * e + 1] * a.scale);
+          st_global_v8(dst + 16 * j, w);
         }
       }
       if (it == 1 && tid == 0) DBG_STAMP(60);
@@ -562,7 +602,12 @@ int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
   CUtensorMap map_qkv, map_do;
   if (make_map_bf16(&map_qkv, a.qkv, rows, 3 * C, 3 * C, npad) != 0) return -54;
   if (make_map_bf16(&map_do, a.d_o, rows, C, C, npad) != 0) return -54;
-  const int smem = 1024 + 4 * npad * 128 + TCB_DS_BYTES + 2048 + 64;
+  int qk_pairs = 2;                                             // prefetch the next head's Q / K when they fit
+  int smem = 1024 + 6 * npad * 128 + TCB_DS_BYTES + 2048 + 128;
+  if (smem > 232448) {
+    qk_pairs = 1;
+    smem = 1024 + 4 * npad * 128 + TCB_DS_BYTES + 2048 + 128;
+  }
   static int configured = 0;
   if (configured < smem) {
     if (cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -52;
@@ -572,7 +617,7 @@ int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
   if (grid > 148) grid = 148;
   attn_delta_kernel<<<static_cast<int>((rows + 7) / 8), 256, 0, st>>>(a.d_o, a.o, a.o_lo, a.delta, static_cast<int>(rows),
                                                                      a.N, a.H);
-  attn_bwd_tc_kernel<<<grid, TCB_THREADS, smem, st>>>(map_qkv, map_do, a, npad);
+  attn_bwd_tc_kernel<<<grid, TCB_THREADS, smem, st>>>(map_qkv, map_do, a, npad, qk_pairs);
   return cudaGetLastError() == cudaSuccess ? 0 : -53;
 }
 int attn_debug_read(long long* out, int n) {

@@ -276,6 +276,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_major(int M, int N, int a
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// 256-bit global store (sm_100: STG.256).  One thread writing a whole 128-byte row costs the LSU one line visit per
+// instruction, so the widest store halves the cost of the per-thread row stores in the attention epilogues.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
 // ---------------------------------------------------------------- small math
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -197,7 +197,9 @@ def test_gemm_adapter_segment_split_precision(K):
 
 
 @pytest.mark.parametrize("B,N,H,D", [(3, 197, 12, 64), (2, 257, 16, 80), (2, 64, 4, 64), (1, 50, 2, 64), (2, 17, 3, 64),
-                                     (1, 128, 2, 80)])
+                                     (1, 128, 2, 80),
+                                     (40, 197, 12, 64),     # 480 heads: every persistent CTA walks over 3-4 heads
+                                     (80, 256, 4, 64)])     # N = 256: single Q/K pair (no prefetch), 2+ heads per CTA
 def test_attention_fwd_bwd(K, B, N, H, D):
     g = torch.Generator(device="cuda").manual_seed(6)
     C = H * D

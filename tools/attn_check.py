@@ -34,6 +34,8 @@ def timeit(B, N, H, D, bwd=True):
     scale = D ** -0.5
     for _ in range(3):
         o, o_lo, lse = K.attn_fwd(qkv.view(-1), B, N, H, D, scale)
+        if bwd:
+            K.attn_bwd(qkv.view(-1), o, o_lo, lse, d_o, B, N, H, D, scale)
     e = [torch.cuda.Event(True) for _ in range(3)]
     e[0].record()
     for _ in range(10):
