@@ -27,6 +27,9 @@ CONFIGS = {
                        batch=256, gflop_per_image=264.60),
     "vith14_r32": dict(model="vit_huge_patch14_224_in21k", embed_dim=1280, depth=32, num_heads=16, patch=14, rank=32,
                        batch=128, gflop_per_image=711.95),
+    # BASELINE.json configs[4]: --evaluate mode, CP delta merged into the frozen weights, inference batch 1024
+    "vitb16_eval": dict(model="vit_base_patch16_224_in21k", embed_dim=768, depth=12, num_heads=12, patch=16, rank=16,
+                        batch=1024, gflop_per_image=35.13, eval=True),
 }
 NUM_CLASSES = 100
 METRIC = "fine-tune images/sec, ViT-B/16 CaRA r16, 1/2/4/8 B200; fused GEMM % TC peak"
@@ -139,6 +142,8 @@ def run_cuda(args):
     cfg = CONFIGS[args.config]
     B = args.batch or cfg["batch"]
     vit, opt = build_model(cfg, dev)
+    if cfg.get("eval"):
+        return run_eval(args, cfg, vit, dev, world, rank)
     img = 224
     g = torch.Generator().manual_seed(4321 + rank)
     host_x = [torch.randn(B, 3, img, img, generator=g).pin_memory() for _ in range(2)]
@@ -265,6 +270,80 @@ def run_cuda(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_eval(args, cfg, vit, dev, world, rank):
+    """--evaluate path (vit_cp.py:168-173, :73-82): merge the CP delta into the frozen weights once
+    (cara_b200.merge.merge_cara), then time plain forwards + arg-max at the config's inference batch."""
+    import torch
+    import torch.distributed as dist
+    from cara_b200 import kernels as K
+    from cara_b200.merge import merge_cara
+    B = args.batch or cfg["batch"]
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    merged = merge_cara(vit)
+    t1.record()
+    torch.cuda.synchronize()
+    merge_ms = t0.elapsed_time(t1)
+    g = torch.Generator().manual_seed(4321 + rank)
+    host_x = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
+    dev_x = [t.to(dev) for t in host_x]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def fwd(x):
+        with torch.no_grad():
+            return vit(x).argmax(1)
+
+    for i in range(args.warmup):
+        fwd(dev_x[i % 2])
+    barrier()
+    launches0 = K.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        pred = fwd(dev_x[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = K.launch_count - launches0
+    stage = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    pred_host = torch.zeros(B, dtype=torch.int64).pin_memory()
+    t0.record()
+    for i in range(args.steps):
+        stage[i % 2].copy_(host_x[i % 2], non_blocking=True)
+        pred_host.copy_(fwd(stage[i % 2]), non_blocking=True)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = [float(v) for v in t]
+    peak_tf, _, peak_src = peaks()
+    total = B * world * args.steps
+    out = {"metric": "eval images/sec, ViT-B/16 CaRA r16 merged (--evaluate)", "value": total / (ms * 1e-3), "unit": "images/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "ViT-B/16 --evaluate forward, CP delta merged into the frozen weights by the reconstruction "
+                                  "kernel, inference batch %d per GPU" % B, "config_key": args.config,
+                      "merged_projections": merged, "merge_ms": merge_ms,
+                      "algorithmic_gflop_per_image": cfg["gflop_per_image"]},
+           "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(host_x[0].numel() * 4),
+                   "d2h_bytes_per_step": B * 8},
+           "gpu_launches": launches,
+           "roofline": {"bound": "tensor", "kernel": "whole eval forward vs dense bf16 peak",
+                        "achieved": cfg["gflop_per_image"] * 1e9 * B / (ms / args.steps * 1e-3) / 1e12, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": cfg["gflop_per_image"] * 1e9 * B / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
+                        "traffic": None, "peak_source": peak_src}}
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
