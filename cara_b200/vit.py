@@ -299,9 +299,84 @@ _GEOMETRY = {
 }
 
 
+def resize_pos_embed(posemb, posemb_new, num_tokens=1, gs_new=()):
+    """timm 0.4.12 ``resize_pos_embed``: keep the class-token rows, bilinearly resample the grid rows."""
+    import math
+    ntok_new = posemb_new.shape[1]
+    tok, grid = (posemb[:, :num_tokens], posemb[0, num_tokens:]) if num_tokens else (posemb[:, :0], posemb[0])
+    ntok_new -= num_tokens
+    gs_old = int(math.sqrt(len(grid)))
+    if not len(gs_new):
+        gs_new = [int(math.sqrt(ntok_new))] * 2
+    grid = grid.reshape(1, gs_old, gs_old, -1).permute(0, 3, 1, 2)
+    grid = nn.functional.interpolate(grid, size=tuple(gs_new), mode="bilinear")
+    grid = grid.permute(0, 2, 3, 1).reshape(1, gs_new[0] * gs_new[1], -1)
+    return torch.cat([tok, grid], dim=1)
+
+
+@torch.no_grad()
+def load_npz_weights(model, checkpoint_path, prefix=""):
+    """Import a JAX/Flax ViT checkpoint (``ViT-B_16.npz`` of vit_cp.py:155) into the timm-layout parameters:
+    the mapping of timm 0.4.12 ``vision_transformer._load_weights`` (un-vendored dependency, restated) --
+    Flax kernels are [in, out] (conv: [P, P, Cin, C]; attention: query/key/value [C, H, D], out [H, D, C]) and
+    are transposed into nn.Linear / nn.Conv2d layout; q, k, v are concatenated into ``qkv``; the position
+    embedding is resampled when the grid differs; the head is copied only when the class counts agree."""
+    import numpy as np
+
+    def n2p(w, t=True):
+        if w.ndim == 4 and w.shape[0] == w.shape[1] == w.shape[2] == 1:
+            w = w.flatten()
+        if t:
+            if w.ndim == 4:
+                w = w.transpose([3, 2, 0, 1])
+            elif w.ndim == 3:
+                w = w.transpose([2, 0, 1])
+            elif w.ndim == 2:
+                w = w.transpose([1, 0])
+        return torch.from_numpy(np.ascontiguousarray(w)).float()
+
+    w = np.load(checkpoint_path)
+    if not prefix and "opt/target/embedding/kernel" in w:
+        prefix = "opt/target/"
+    conv = n2p(w[prefix + "embedding/kernel"])
+    if conv.shape[1] != model.patch_embed.proj.weight.shape[1]:
+        raise ValueError("input channels of the checkpoint (%d) differ from the model's" % conv.shape[1])
+    model.patch_embed.proj.weight.copy_(conv)
+    model.patch_embed.proj.bias.copy_(n2p(w[prefix + "embedding/bias"]))
+    model.cls_token.copy_(n2p(w[prefix + "cls"], t=False))
+    pos = n2p(w[prefix + "Transformer/posembed_input/pos_embedding"], t=False)
+    if pos.shape != model.pos_embed.shape:
+        pos = resize_pos_embed(pos, model.pos_embed, getattr(model, "num_tokens", 1), model.patch_embed.grid_size)
+    model.pos_embed.copy_(pos)
+    model.norm.weight.copy_(n2p(w[prefix + "Transformer/encoder_norm/scale"]))
+    model.norm.bias.copy_(n2p(w[prefix + "Transformer/encoder_norm/bias"]))
+    if isinstance(model.head, nn.Linear) and (prefix + "head/bias") in w and \
+            model.head.bias.shape[0] == w[prefix + "head/bias"].shape[-1]:
+        model.head.weight.copy_(n2p(w[prefix + "head/kernel"]))
+        model.head.bias.copy_(n2p(w[prefix + "head/bias"]))
+    for i, block in enumerate(model.blocks.children()):
+        bp = "%sTransformer/encoderblock_%d/" % (prefix, i)
+        mp = bp + "MultiHeadDotProductAttention_1/"
+        block.norm1.weight.copy_(n2p(w[bp + "LayerNorm_0/scale"]))
+        block.norm1.bias.copy_(n2p(w[bp + "LayerNorm_0/bias"]))
+        block.attn.qkv.weight.copy_(torch.cat([n2p(w[mp + n + "/kernel"], t=False).flatten(1).T
+                                               for n in ("query", "key", "value")]))
+        block.attn.qkv.bias.copy_(torch.cat([n2p(w[mp + n + "/bias"], t=False).reshape(-1)
+                                             for n in ("query", "key", "value")]))
+        block.attn.proj.weight.copy_(n2p(w[mp + "out/kernel"]).flatten(1))
+        block.attn.proj.bias.copy_(n2p(w[mp + "out/bias"]))
+        for r in range(2):
+            lin = getattr(block.mlp, "fc%d" % (r + 1))
+            lin.weight.copy_(n2p(w[bp + "MlpBlock_3/Dense_%d/kernel" % r]))
+            lin.bias.copy_(n2p(w[bp + "MlpBlock_3/Dense_%d/bias" % r]))
+        block.norm2.weight.copy_(n2p(w[bp + "LayerNorm_2/scale"]))
+        block.norm2.bias.copy_(n2p(w[bp + "LayerNorm_2/bias"]))
+    return model
+
+
 def create_model(model_name, pretrained=False, checkpoint_path="", **kwargs):
-    """``timm.models.create_model`` for the ViT names the reference uses (random init; ``checkpoint_path``
-    accepts a torch state_dict file -- the JAX .npz import of vit_cp.py:155 is out of scope)."""
+    """``timm.models.create_model`` for the ViT names the reference uses.  ``checkpoint_path``: a JAX ``.npz``
+    (vit_cp.py:155, imported by ``load_npz_weights``) or a torch state_dict file."""
     if model_name not in _GEOMETRY:
         raise RuntimeError("Unknown model (%s)" % model_name)
     if pretrained:
@@ -310,12 +385,15 @@ def create_model(model_name, pretrained=False, checkpoint_path="", **kwargs):
     cfg.update(kwargs)
     model = VisionTransformer(**cfg)
     if checkpoint_path:
-        if str(checkpoint_path).endswith(".npz"):
+        if str(checkpoint_path).lower().endswith((".npz", ".npy")):
             import os
             import warnings
             if os.path.exists(checkpoint_path):
-                raise NotImplementedError("JAX .npz checkpoint import is not implemented (SURVEY 8f item 1)")
-            warnings.warn("checkpoint %r not found: keeping random-init weights" % (checkpoint_path,))
+                load_npz_weights(model, checkpoint_path)
+            else:
+                # the reference's entry point hard-codes ./ViT-B_16.npz (vit_cp.py:155); without the file (no
+                # network here) the synthetic runs keep the random initialisation
+                warnings.warn("checkpoint %r not found: keeping random-init weights" % (checkpoint_path,))
         else:
             model.load_state_dict(torch.load(checkpoint_path, map_location="cpu"), strict=False)
     return model

@@ -111,3 +111,49 @@ def test_vtab_config_and_cli_surface():
     assert len(mod.config) == 19
     for name, c in mod.config.items():
         assert set(c) == {"init_mean", "init_std", "scale", "seed", "logger"}, name
+
+
+def test_npz_checkpoint_import_roundtrip(tmp_path):
+    """vit_cp.py:155 loads ./ViT-B_16.npz through timm's JAX importer: write a Flax-layout .npz from a random
+    model (inverse mapping, independent code) and check create_model(checkpoint_path=...) reproduces every
+    parameter, including a position-embedding grid resample and the skipped head on a class-count mismatch."""
+    import numpy as np
+    import torch
+    from cara_b200.vit import create_model
+    torch.manual_seed(3)
+    C, H, L = 64, 4, 2
+    src = create_model("vit_base_patch16_224_in21k", embed_dim=C, depth=L, num_heads=H, num_classes=7, img_size=32)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.copy_(torch.randn_like(p))
+    sd = {k: v.detach().numpy() for k, v in src.state_dict().items()}
+    z = {"embedding/kernel": sd["patch_embed.proj.weight"].transpose(2, 3, 1, 0), "embedding/bias": sd["patch_embed.proj.bias"],
+         "cls": sd["cls_token"], "Transformer/posembed_input/pos_embedding": sd["pos_embed"],
+         "Transformer/encoder_norm/scale": sd["norm.weight"], "Transformer/encoder_norm/bias": sd["norm.bias"],
+         "head/kernel": sd["head.weight"].T, "head/bias": sd["head.bias"]}
+    D = C // H
+    for i in range(L):
+        b, m = "Transformer/encoderblock_%d/" % i, "Transformer/encoderblock_%d/MultiHeadDotProductAttention_1/" % i
+        t = "blocks.%d." % i
+        z[b + "LayerNorm_0/scale"], z[b + "LayerNorm_0/bias"] = sd[t + "norm1.weight"], sd[t + "norm1.bias"]
+        z[b + "LayerNorm_2/scale"], z[b + "LayerNorm_2/bias"] = sd[t + "norm2.weight"], sd[t + "norm2.bias"]
+        for j, n in enumerate(("query", "key", "value")):
+            z[m + n + "/kernel"] = sd[t + "attn.qkv.weight"][j * C:(j + 1) * C].T.reshape(C, H, D)
+            z[m + n + "/bias"] = sd[t + "attn.qkv.bias"][j * C:(j + 1) * C].reshape(H, D)
+        z[m + "out/kernel"] = sd[t + "attn.proj.weight"].T.reshape(H, D, C)
+        z[m + "out/bias"] = sd[t + "attn.proj.bias"]
+        for r in range(2):
+            z[b + "MlpBlock_3/Dense_%d/kernel" % r] = sd[t + "mlp.fc%d.weight" % (r + 1)].T
+            z[b + "MlpBlock_3/Dense_%d/bias" % r] = sd[t + "mlp.fc%d.bias" % (r + 1)]
+    path = str(tmp_path / "ViT-tiny.npz")
+    np.savez(path, **z)
+    dst = create_model("vit_base_patch16_224_in21k", checkpoint_path=path, embed_dim=C, depth=L, num_heads=H,
+                       num_classes=7, img_size=32)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    # other class count: head keeps its own init; other image size: grid rows are resampled, class token row kept
+    dst2 = create_model("vit_base_patch16_224_in21k", checkpoint_path=path, embed_dim=C, depth=L, num_heads=H,
+                        num_classes=5, img_size=64)
+    assert dst2.head.weight.shape == (5, C) and dst2.pos_embed.shape == (1, 17, C)
+    assert torch.equal(dst2.pos_embed[:, 0], src.pos_embed[:, 0])
+    assert torch.equal(dst2.blocks[1].mlp.fc2.weight, src.blocks[1].mlp.fc2.weight)
