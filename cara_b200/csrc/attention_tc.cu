@@ -384,13 +384,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           mbar_wait(bar_pds, n & 1u);                           // P^T is in TMEM, dS^T in shared memory
           tc_fence_after();
           if (it == 1) DBG_STAMP(2 + 8 * t);
-          for (int j = 0; j < ksteps; ++j) {                    // dV_t = P^T dO   (K = queries)
+          // dV_t and dK_t alternate so that consecutive MMAs never accumulate into the same TMEM tile
+          for (int j = 0; j < ksteps; ++j) {                    // dV_t = P^T dO,  dK_t = dS^T Q   (K = queries)
             const uint32_t pcol = 16 * j < c_split ? 8u * j : static_cast<uint32_t>(c_split + 8 * (j - c_split / 16));
             umma_bf16_ts(tmem_base + TCB_DV_COL, tmem_base + pcol,
                          umma_desc_mn_sw128(sDO + static_cast<uint32_t>(j) * 2048u, tile_bytes, 1024u), idesc_dv,
                          j != 0 ? 1u : 0u);
-          }
-          for (int j = 0; j < ksteps; ++j) {                    // dK_t = dS^T Q   (K = queries)
             umma_bf16(tmem_base + TCB_DK_COL,
                       umma_desc_sw128(sDS + static_cast<uint32_t>(j >> 2) * 16384u + static_cast<uint32_t>(j & 3) * 32u),
                       umma_desc_mn_sw128(sQ + static_cast<uint32_t>(j) * 2048u, tile_bytes, 1024u), idesc_dk,
@@ -398,8 +397,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           }
           umma_commit(bar_kv);                                  // dK_t / dV_t can be read out while dQ still runs
           const int kk = (npad - 128 * t < 128 ? npad - 128 * t : 128) / 16;   // valid keys of this tile / 16
-          for (int m = 0; m < nt; ++m) {                        // dQ_m = dS K_t   (K = keys of tile t)
-            for (int j = 0; j < kk; ++j) {
+          for (int j = 0; j < kk; ++j) {                        // dQ_m = dS K_t   (K = keys of tile t), m interleaved
+            for (int m = 0; m < nt; ++m) {
               umma_bf16(tmem_base + TCB_DQ_COL + 64u * m,
                         umma_desc_mn_sw128(sDS + static_cast<uint32_t>(2 * m) * 16384u + static_cast<uint32_t>(j) * 2048u,
                                            16384u, 1024u),

@@ -126,12 +126,13 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink
         zs = torch.split(z, sizes)
         dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
         colsum = zs[3] if need_bias else None
+    # the three readers of G run back to back: for the C-wide projections G (77 MB at ViT-B) stays in the 126 MB L2
     dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
+    K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
     dx = None
     if need_dx:
         dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux)
     K.adapter_cols(x, dT, 1, Rp, out=dA)
-    K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
     if sink is not None:
         return (dx,) + sink[0].release(sink[1], R, need_bias)
     return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum

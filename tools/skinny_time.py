@@ -4,7 +4,10 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cara_b200 import kernels as K
 M, Rp = 50432, 16
+ONCE = os.environ.get("SKINNY_ONCE") == "1"      # ncu mode: one launch per configuration
 def t(fn, n=10):
+    if ONCE:
+        fn(); torch.cuda.synchronize(); return 1.0
     for _ in range(3): fn()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
