@@ -277,7 +277,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const uint32_t stats = sDS + TCB_DS_BYTES;                 // nlse[256], delta[256] (fp32)
   const uint32_t bars = stats + 2048u;
   const uint32_t bar_sdp = bars + 8, bar_pds = bars + 16, bar_kv = bars + 24, bar_out = bars + 32,
-                 bar_rd = bars + 40, tmem_slot = bars + 48, bar_qk0 = bars + 56, bar_v = bars + 72, bar_do = bars + 80;
+                 bar_rd = bars + 40, tmem_slot = bars + 48, bar_qk0 = bars + 56, bar_v = bars + 72, bar_do = bars + 80,
+                 bar_pds0 = bars + 88;
   float* s_nlse = reinterpret_cast<float*>(smem_raw + (stats - raw));
   float* s_delta = s_nlse + 256;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -286,7 +287,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const int N = a.N, C = a.H * TC_D;
   const int nt = (N + 127) / 128;                              // key tiles == query tiles
   const int ksteps = npad / 16;
-  const int c_split = ((ksteps + 1) / 2) * 16;                 // query columns [0, c_split) | [c_split, npad)
+  // The query columns are worked through in two phases so that the dV / dK MMAs over the first 128 queries run
+  // while the compute warps are still busy with the rest: phase 0 = queries [0, qa), phase 1 = [128, npad); in each
+  // phase compute half 0 takes the lower part and half 1 the upper part.  Every (phase, half) segment
+  // [sb, se) packs its P^T into TMEM columns [sb, sb + (se - sb) / 2) -- inside its own, already consumed, scores.
+  const int qa = npad < 128 ? npad : 128;
+  const int a_split = ((qa / 16 + 1) / 2) * 16;
+  const int r_split = 128 + (((npad - qa) / 16 + 1) / 2) * 16;
   const int heads = a.B * a.H;
 
   if (warp == 8) {
@@ -299,6 +306,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       mbar_init(bar_do, 1);
       mbar_init(bar_sdp, 1);
       mbar_init(bar_pds, 256);
+      mbar_init(bar_pds0, 256);
       mbar_init(bar_kv, 1);
       mbar_init(bar_out, 1);
       mbar_init(bar_rd, 256);
@@ -381,20 +389,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             mbar_wait(bar_sdp, n & 1u);
             load_v(next);
           }
-          mbar_wait(bar_pds, n & 1u);                           // P^T is in TMEM, dS^T in shared memory
-          tc_fence_after();
-          if (it == 1) DBG_STAMP(2 + 8 * t);
-          // dV_t and dK_t alternate so that consecutive MMAs never accumulate into the same TMEM tile
-          for (int j = 0; j < ksteps; ++j) {                    // dV_t = P^T dO,  dK_t = dS^T Q   (K = queries)
-            const uint32_t pcol = 16 * j < c_split ? 8u * j : static_cast<uint32_t>(c_split + 8 * (j - c_split / 16));
-            umma_bf16_ts(tmem_base + TCB_DV_COL, tmem_base + pcol,
+          // dV_t = P^T dO,  dK_t = dS^T Q   (K = queries): the k-steps of phase 0 start as soon as both compute
+          // halves are done with the first 128 queries (whose dP^T columns the two accumulators overlay)
+          auto dv_dk = [&](int j) {
+            const int c = 16 * j;
+            const int sb = c < a_split ? 0 : (c < qa ? a_split : (c < r_split ? 128 : r_split));
+            umma_bf16_ts(tmem_base + TCB_DV_COL, tmem_base + static_cast<uint32_t>(sb + ((c - sb) >> 1)),
                          umma_desc_mn_sw128(sDO + static_cast<uint32_t>(j) * 2048u, tile_bytes, 1024u), idesc_dv,
                          j != 0 ? 1u : 0u);
             umma_bf16(tmem_base + TCB_DK_COL,
                       umma_desc_sw128(sDS + static_cast<uint32_t>(j >> 2) * 16384u + static_cast<uint32_t>(j & 3) * 32u),
                       umma_desc_mn_sw128(sQ + static_cast<uint32_t>(j) * 2048u, tile_bytes, 1024u), idesc_dk,
                       j != 0 ? 1u : 0u);
-          }
+          };
+          mbar_wait(bar_pds0, n & 1u);                          // P^T / dS^T of queries [0, qa) are in place
+          tc_fence_after();
+          for (int j = 0; j < qa / 16; ++j) dv_dk(j);
+          mbar_wait(bar_pds, n & 1u);                           // ... and the rest
+          tc_fence_after();
+          if (it == 1) DBG_STAMP(2 + 8 * t);
+          for (int j = qa / 16; j < ksteps; ++j) dv_dk(j);
           umma_commit(bar_kv);                                  // dK_t / dV_t can be read out while dQ still runs
           const int kk = (npad - 128 * t < 128 ? npad - 128 * t : 128) / 16;   // valid keys of this tile / 16
           for (int j = 0; j < kk; ++j) {                        // dQ_m = dS K_t   (K = keys of tile t), m interleaved
@@ -426,7 +440,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const int key_local = q4 * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     const float sl2 = a.scale * 1.4426950408889634f;
-    const int c_begin = half == 0 ? 0 : c_split, c_end = half == 0 ? c_split : npad;
     const uint32_t ds_row = sDS + static_cast<uint32_t>(key_local) * 128u;
     const uint32_t sw = static_cast<uint32_t>(key_local & 7);
     uint32_t n = 0, it = 0;
@@ -452,8 +465,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         mbar_wait(bar_sdp, n & 1u);
         tc_fence_after();
         if (it == 1 && tid == 0) DBG_STAMP(33 + 8 * t);
-        if (warp_live) {
-          for (int c = c_begin; c < c_end; c += 16) {
+        // one (phase, half) segment [cb, ce) of the query columns, P^T packed from column cb on
+        auto segment = [&](int cb, int ce) {
+          for (int c = cb; c < ce; c += 16) {
             uint32_t s[16], dp[16], pk[8], dsk[8];
             tmem_ld16(lane_addr + c, s);
             tmem_ld16(lane_addr + TCB_DP_COL + c, dp);
@@ -474,7 +488,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
               dsk[2 * j4] = pack_bf16(d0, d1); dsk[2 * j4 + 1] = pack_bf16(d2, d3);
             }
             // P^T: 16 queries of this key -> 8 packed columns on top of already consumed scores
-            tmem_st8(lane_addr + (half == 0 ? (c >> 1) : c_split + ((c - c_split) >> 1)), pk);
+            tmem_st8(lane_addr + static_cast<uint32_t>(cb + ((c - cb) >> 1)), pk);
             // dS^T: two 16-byte chunks of row `key_local` in query block c / 64
             const uint32_t blk = ds_row + static_cast<uint32_t>(c >> 6) * 16384u;
             const uint32_t ch = static_cast<uint32_t>((c & 63) >> 3);
@@ -486,7 +500,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           // keys in [N, npad) are padding: their rows of dS^T feed dQ and must be exactly zero (their scores are
           // finite garbage -- the next sample's rows -- so the values written above may be anything, even inf/nan)
           if (!key_ok) {
-            for (int c = c_begin; c < c_end; c += 8) {
+            for (int c = cb; c < ce; c += 8) {
               const uint32_t blk = ds_row + static_cast<uint32_t>(c >> 6) * 16384u;
               const uint32_t ch = static_cast<uint32_t>((c & 63) >> 3);
               asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(blk + ((ch ^ sw) << 4)), "r"(0u) : "memory");
@@ -494,7 +508,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           }
           tmem_st_wait();
           fence_proxy_async();                                  // dS^T stores -> visible to the tensor core (async proxy)
-        }
+        };
+        if (warp_live) segment(half == 0 ? 0 : a_split, half == 0 ? a_split : qa);
+        tc_fence_before();
+        mbar_arrive(bar_pds0);
+        if (warp_live) segment(half == 0 ? 128 : r_split, half == 0 ? r_split : npad);
         tc_fence_before();
         mbar_arrive(bar_pds);
         if (it == 1 && tid == 0) DBG_STAMP(34 + 8 * t);
