@@ -35,6 +35,17 @@ NUM_CLASSES = 100
 METRIC = "fine-tune images/sec, ViT-B/16 CaRA r16, 1/2/4/8 B200; fused GEMM % TC peak"
 
 
+def gemm_traffic(config_key):
+    """DRAM bytes per gemm_cp_kernel launch (launch-weighted over one step) from the committed ncu --set full
+    captures (profiles/r01_traffic.json); None when no capture exists for this configuration."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if d.get("config_key") == config_key:
+            return float(d["avg_dram_bytes_per_launch"])
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -263,7 +274,9 @@ def run_cuda(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_cp_kernel (fused CP projections fwd + dX, %d launches over 2 eagerly enqueued steps)" % len(gemm_events),
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": gemm_traffic(args.config), "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json)",
+                     "algorithmic_flops_per_launch": gemm_flops / max(1, len(gemm_events)),
+                     "peak_source": peak_src,
                      "step_frac_of_peak": cfg["gflop_per_image"] * 1e9 * B / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
         "loss": loss_value,
     }

@@ -38,6 +38,11 @@ class DropPath(nn.Module):
     def rowscale(self, batch, device):
         if not self.training or not self.drop_prob:
             return None
+        pre = self.__dict__.get("_predrawn")
+        if pre:                                    # drawn for all blocks at once by VisionTransformer.forward
+            rs = pre.pop(0)
+            if rs.shape[0] == batch and rs.device == device:
+                return rs
         keep = 1.0 - self.drop_prob
         return torch.floor(keep + torch.rand(batch, device=device, dtype=F32)) / keep
 
@@ -266,6 +271,7 @@ class VisionTransformer(nn.Module):
             else:
                 x = K.assemble_tokens(pe.reshape(-1, C), self.cls_token.detach().reshape(C).float().contiguous(),
                                       self.pos_embed.detach().reshape(N, C).float().contiguous(), B, N, C)
+        self._predraw_droppath(B, x.device)
         pending = None
         for blk in self.blocks:
             if pending is None:
@@ -282,6 +288,26 @@ class VisionTransformer(nn.Module):
             xc = xc + (d if pending[1] is None else d * pending[1][:, None])
         hc = ops.LayerNormFunction.apply(xc.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps, F32)
         return self.pre_logits(hc)
+
+    def _predraw_droppath(self, B, device):
+        """Stochastic depth draws two per-sample multipliers per block (timm drop_path); draw all of them with
+        one rand / add / floor / div instead of four tiny kernels per use."""
+        dps = [blk.drop_path for blk in self.blocks if isinstance(blk.drop_path, DropPath)]
+        for dp in dps:
+            dp.__dict__["_predrawn"] = None
+        dps = [dp for dp in dps if dp.training and dp.drop_prob]
+        if not dps:
+            return
+        key = (str(device), tuple(float(dp.drop_prob) for dp in dps))
+        cache = self.__dict__.get("_cara_dp_keep")
+        if cache is None or cache[0] != key:       # host -> device copy: once, never inside a graph capture
+            keep = torch.tensor([1.0 - p for p in key[1] for _ in range(2)], device=device, dtype=F32).view(-1, 1)
+            cache = (key, keep)
+            self.__dict__["_cara_dp_keep"] = cache
+        keep = cache[1]
+        rs = torch.floor(keep + torch.rand(keep.shape[0], B, device=device, dtype=F32)) / keep
+        for i, dp in enumerate(dps):
+            dp.__dict__["_predrawn"] = [rs[2 * i], rs[2 * i + 1]]
 
     def forward(self, x):
         f = self.forward_features(x)
