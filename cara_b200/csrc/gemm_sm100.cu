@@ -225,7 +225,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint4* src = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow < p.M ? grow : 0) * p.ldaux +
                                                           tc.n0 + c_first * EC);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ux[j] = __ldg(src + j);
+        for (int j = 0; j < 4; ++j) ld_global_nc_v8(src + 2 * j, ux[2 * j], ux[2 * j + 1]);
       }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
@@ -272,7 +272,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint4* src = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow < p.M ? grow : 0) * p.ldaux +
                                                               n + EC);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ux[j] = __ldg(src + j);
+            for (int j = 0; j < 4; ++j) ld_global_nc_v8(src + 2 * j, ux[2 * j], ux[2 * j + 1]);
           }
         } else {
 #pragma unroll

@@ -32,11 +32,20 @@ __device__ __forceinline__ void gelu_terms(float a, float& w, float& e) {
   const float z = a * 0.84932180028801904f;          // sqrt(log2(e) / 2): e = 2^(-z^2) = exp(-a^2 / 2)
   e = exp2f(-z * z);
 }
+// Forward epilogue form with ONE MUFU and 9 FP32 instructions (the fc1 epilogue is issue-bound):
+//   GELU(u) = max(u, 0) - a Phi(-a),  a = |u|,  Phi(-a) = erfc(a / sqrt 2) / 2 = 2^q(a)
+// q = degree-6 polynomial fitted (weighted least squares on Chebyshev nodes of [0, 6], weight a Phi(-a)) to
+// log2(erfc(a / sqrt 2) / 2); a is clamped at 6 (Phi(-6) = 1e-9).  |abs err| <= 4e-7 against the exact-erf GELU over
+// [-12, 12] in fp32 (tools/gelu_fit.py), the same class as the A&S form used for the derivative.
 __device__ __forceinline__ float gelu_fast(float u) {
-  const float a = fabsf(u);
-  float w, e;
-  gelu_terms(a, w, e);
-  return fmaf(-0.5f * a * w, e, fmaxf(u, 0.0f));
+  const float a = fminf(fabsf(u), 6.0f);
+  float q = fmaf(a, 3.042068784e-05f, -7.316191914e-04f);
+  q = fmaf(a, q, 7.908979431e-03f);
+  q = fmaf(a, q, -5.307019129e-02f);
+  q = fmaf(a, q, -4.590840042e-01f);
+  q = fmaf(a, q, -1.151080370e+00f);
+  q = fmaf(a, q, -1.000007629e+00f);
+  return fmaf(-a, exp2f(q), fmaxf(u, 0.0f));
 }
 __device__ __forceinline__ float gelu_grad_fast(float u) {
   const float a = fabsf(u);

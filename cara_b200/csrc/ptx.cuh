@@ -283,6 +283,12 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+// 256-bit read-only global load (sm_100: LDG.256): halves the line visits of per-thread row reads.
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+
 // ---------------------------------------------------------------- small math
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
