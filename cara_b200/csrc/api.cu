@@ -73,7 +73,7 @@ int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At,
   a.X = static_cast<const bf16*>(X); a.ldx = ldx; a.M = M; a.kslice = K;
   a.Ft = static_cast<const bf16*>(At); a.ldf = K; a.scales = scales; a.mode = 0; a.s_out = slices;
   a.T = T; a.U = static_cast<bf16*>(Uhat); a.ldu = static_cast<long>(slices) * 3 * Rp; a.dc = nullptr;
-  CARA_RET(cara::rows_launch(a, Rp, 1, CARA_STREAM(stream)), "cara_adapter_rows_fwd");
+  CARA_RET(cara::rows_launch(a, Rp, 1, 0, CARA_STREAM(stream)), "cara_adapter_rows_fwd");
 }
 int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int slices, const void* Bt, const float* scales,
                           int Rp, const float* T, void* dThat, float* dscales, void* stream) {
@@ -82,7 +82,7 @@ int cara_adapter_rows_bwd(const void* G, long ldg, int M, int N, int slices, con
   a.X = static_cast<const bf16*>(G); a.ldx = ldg; a.M = M; a.kslice = N / slices;
   a.Ft = static_cast<const bf16*>(Bt); a.ldf = N / slices; a.scales = scales; a.mode = 1; a.s_out = 0;
   a.T = const_cast<float*>(T); a.U = static_cast<bf16*>(dThat); a.ldu = 3 * Rp; a.dc = dscales;
-  CARA_RET(cara::rows_launch(a, Rp, slices, CARA_STREAM(stream)), "cara_adapter_rows_bwd");
+  CARA_RET(cara::rows_launch(a, Rp, slices, 0, CARA_STREAM(stream)), "cara_adapter_rows_bwd");
 }
 int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const void* V, long ldv, int slices, int Rp, float* out,
                       float* colsum, void* stream) {

@@ -28,8 +28,9 @@ struct RowsArgs {
   float* T;                                              // [M, Rp] fp32 (fwd: out, bwd: in)
   __nv_bfloat16* U; long ldu;                            // fwd Uhat [M, s_out*Rp] / bwd dThat [M, Rp]
   float* dc;                                             // bwd [CS, Rp], atomically accumulated
+  int rows_per_cta;                                      // set by rows_launch (<= 128)
 };
-int rows_launch(const RowsArgs& a, int rp, int cs, cudaStream_t st);
+int rows_launch(const RowsArgs& a, int rp, int cs, int num_sms, cudaStream_t st);
 
 struct ColsArgs {
   const __nv_bfloat16* X; long ldx; int M; int Kc;      // X [M, Kc]

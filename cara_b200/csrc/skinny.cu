@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -50,10 +51,13 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------ rows_kernel
-constexpr int R_BM = 128, R_BK = 64, R_STAGES = 3;   // 3 x 20 KB: three CTAs per SM => M = 50k tokens is one wave
+// Every CTA owns the same number of rows (<= 128: eight warps x one 16-row MMA tile) and the grid is exactly
+// CTAs-per-SM x SMs, so all SMs stream the same number of bytes: with 128-row tiles M = 50,432 gave 394 CTAs on 444
+// slots, a third CTA on 98 SMs and the other 50 SMs idle for a third of the launch.
+constexpr int R_BM = 128, R_BK = 64, R_STAGES = 3;   // 3 x 20 KB: three CTAs per SM
 
 template <int RT, int CS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 rows_kernel(const RowsArgs a) {
   constexpr int RP = RT * 8;
   constexpr int NT = 2 * RT;                       // n-tiles incl. the lo halves of the factor
@@ -64,7 +68,8 @@ rows_kernel(const RowsArgs a) {
   __shared__ float red[CS * RP];
   const uint32_t sbase = s_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * R_BM;
+  const int m0 = blockIdx.x * a.rows_per_cta;
+  const int m_end = min(a.M, m0 + a.rows_per_cta);
   const int cps = a.kslice / R_BK;                 // chunks per slice
   const int nch = CS * cps;
 
@@ -76,7 +81,7 @@ rows_kernel(const RowsArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int idx = j * 256 + tid, row = idx >> 3, ch = idx & 7;
-        const bool ok = (m0 + row) < a.M;
+        const bool ok = (m0 + row) < m_end;
         const __nv_bfloat16* src = a.X + static_cast<size_t>(ok ? m0 + row : 0) * a.ldx + kcol + ch * 8;
         cp_async16(xs + row * 128 + ((ch ^ (row & 7)) << 4), src, ok);
       }
@@ -88,18 +93,43 @@ rows_kernel(const RowsArgs a) {
     cp_async_commit();
   };
 
-  float acc[CS][NT][4];
+  const int g = lane >> 2, t = lane & 3;
+  const int r_lo = m0 + warp * 16 + g, r_hi = r_lo + 8;
+  const bool ok_lo = r_lo < m_end, ok_hi = r_hi < m_end;
+  // emit v as the bf16 column blocks [hi | lo | hi] at row pointer p (block pitch RP)
+  auto emit = [&](__nv_bfloat16* p, int col, float v0, float v1) {
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+    const float2 hf = __bfloat1622float2(hi);
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint32_t*>(p + col) = h;
+    *reinterpret_cast<uint32_t*>(p + RP + col) = pack2(v0 - hf.x, v1 - hf.y);
+    *reinterpret_cast<uint32_t*>(p + 2 * RP + col) = h;
+  };
+
+  // backward: the saved T rows of this thread and the running dThat = sum_s cs_s (.) dU_s
+  float2 t_lo[RT], t_hi[RT];
+  float d[RT][4];
+  if (a.mode != 0) {
+    for (int i = tid; i < CS * RP; i += 256) red[i] = 0.f;
 #pragma unroll
-  for (int s = 0; s < CS; ++s)
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[s][j][e] = 0.f;
+    for (int j = 0; j < RT; ++j) {
+      const int col = j * 8 + 2 * t;
+      t_lo[j] = ok_lo ? *reinterpret_cast<const float2*>(a.T + static_cast<size_t>(r_lo) * RP + col) : make_float2(0.f, 0.f);
+      t_hi[j] = ok_hi ? *reinterpret_cast<const float2*>(a.T + static_cast<size_t>(r_hi) * RP + col) : make_float2(0.f, 0.f);
+      d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
+    }
+  }
 
   for (int i = 0; i < R_STAGES - 1; ++i) issue(i);
 
-#pragma unroll
+  // one slice at a time through ONE set of accumulators (CS x fewer registers: three CTAs per SM for every CS)
+#pragma unroll 1
   for (int s = 0; s < CS; ++s) {
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
     for (int c = 0; c < cps; ++c) {
       const int i = s * cps + c;
       cp_async_wait<R_STAGES - 2>();
@@ -118,63 +148,39 @@ rows_kernel(const RowsArgs a) {
           uint32_t bf[4];
           const int n = jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, ch = kk * 2 + ((lane >> 3) & 1);
           ldsm_x4(fs + n * 128 + ((ch ^ (n & 7)) << 4), bf);
-          mma_bf16(acc[s][jp * 2 + 0], af, bf[0], bf[1]);
-          mma_bf16(acc[s][jp * 2 + 1], af, bf[2], bf[3]);
+          mma_bf16(acc[jp * 2 + 0], af, bf[0], bf[1]);
+          mma_bf16(acc[jp * 2 + 1], af, bf[2], bf[3]);
         }
       }
     }
-  }
-  cp_async_wait<0>();
-
-  const int g = lane >> 2, t = lane & 3;
-  const int r_lo = m0 + warp * 16 + g, r_hi = r_lo + 8;
-  const bool ok_lo = r_lo < a.M, ok_hi = r_hi < a.M;
-  // fold the (factor hi, factor lo) partial products
-#pragma unroll
-  for (int s = 0; s < CS; ++s)
+    // fold the (factor hi, factor lo) partial products
 #pragma unroll
     for (int j = 0; j < RT; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[s][j][e] += acc[s][j + RT][e];
-  // emit v as the bf16 column blocks [hi | lo | hi] at row pointer p (block pitch RP)
-  auto emit = [&](__nv_bfloat16* p, int col, float v0, float v1) {
-    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
-    const float2 hf = __bfloat1622float2(hi);
-    const uint32_t h = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint32_t*>(p + col) = h;
-    *reinterpret_cast<uint32_t*>(p + RP + col) = pack2(v0 - hf.x, v1 - hf.y);
-    *reinterpret_cast<uint32_t*>(p + 2 * RP + col) = h;
-  };
-  if (a.mode == 0) {
-    // forward: T (fp32) and the per-slice scaled operand for the GEMM's adapter segment
+      for (int e = 0; e < 4; ++e) acc[j][e] += acc[j + RT][e];
+    if (a.mode == 0) {
+      // forward (CS == 1): T (fp32) and the per-slice scaled operand for the GEMM's adapter segment
 #pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      const int col = j * 8 + 2 * t;
-      if (ok_lo) *reinterpret_cast<float2*>(a.T + static_cast<size_t>(r_lo) * RP + col) = make_float2(acc[0][j][0], acc[0][j][1]);
-      if (ok_hi) *reinterpret_cast<float2*>(a.T + static_cast<size_t>(r_hi) * RP + col) = make_float2(acc[0][j][2], acc[0][j][3]);
-      for (int so = 0; so < a.s_out; ++so) {
-        const float2 sc = *reinterpret_cast<const float2*>(a.scales + so * RP + col);
-        if (ok_lo) emit(a.U + static_cast<size_t>(r_lo) * a.ldu + so * 3 * RP, col, sc.x * acc[0][j][0], sc.y * acc[0][j][1]);
-        if (ok_hi) emit(a.U + static_cast<size_t>(r_hi) * a.ldu + so * 3 * RP, col, sc.x * acc[0][j][2], sc.y * acc[0][j][3]);
+      for (int j = 0; j < RT; ++j) {
+        const int col = j * 8 + 2 * t;
+        if (ok_lo) *reinterpret_cast<float2*>(a.T + static_cast<size_t>(r_lo) * RP + col) = make_float2(acc[j][0], acc[j][1]);
+        if (ok_hi) *reinterpret_cast<float2*>(a.T + static_cast<size_t>(r_hi) * RP + col) = make_float2(acc[j][2], acc[j][3]);
+        for (int so = 0; so < a.s_out; ++so) {
+          const float2 sc = *reinterpret_cast<const float2*>(a.scales + so * RP + col);
+          if (ok_lo) emit(a.U + static_cast<size_t>(r_lo) * a.ldu + so * 3 * RP, col, sc.x * acc[j][0], sc.y * acc[j][1]);
+          if (ok_hi) emit(a.U + static_cast<size_t>(r_hi) * a.ldu + so * 3 * RP, col, sc.x * acc[j][2], sc.y * acc[j][3]);
+        }
       }
-    }
-  } else {
-    for (int i = tid; i < CS * RP; i += 256) red[i] = 0.f;
-    __syncthreads();
+    } else {
+      if (s == 0) __syncthreads();                 // red[] zero fill (the main loop has at least one barrier anyway)
 #pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      const int col = j * 8 + 2 * t;
-      float2 t_lo = make_float2(0.f, 0.f), t_hi = make_float2(0.f, 0.f);
-      if (ok_lo) t_lo = *reinterpret_cast<const float2*>(a.T + static_cast<size_t>(r_lo) * RP + col);
-      if (ok_hi) t_hi = *reinterpret_cast<const float2*>(a.T + static_cast<size_t>(r_hi) * RP + col);
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-      for (int s = 0; s < CS; ++s) {
+      for (int j = 0; j < RT; ++j) {
+        const int col = j * 8 + 2 * t;
         const float2 sc = *reinterpret_cast<const float2*>(a.scales + s * RP + col);
-        d0 = fmaf(sc.x, acc[s][j][0], d0); d1 = fmaf(sc.y, acc[s][j][1], d1);
-        d2 = fmaf(sc.x, acc[s][j][2], d2); d3 = fmaf(sc.y, acc[s][j][3], d3);
-        float p0 = acc[s][j][0] * t_lo.x + acc[s][j][2] * t_hi.x;
-        float p1 = acc[s][j][1] * t_lo.y + acc[s][j][3] * t_hi.y;
+        d[j][0] = fmaf(sc.x, acc[j][0], d[j][0]); d[j][1] = fmaf(sc.y, acc[j][1], d[j][1]);
+        d[j][2] = fmaf(sc.x, acc[j][2], d[j][2]); d[j][3] = fmaf(sc.y, acc[j][3], d[j][3]);
+        float p0 = acc[j][0] * t_lo[j].x + acc[j][2] * t_hi[j].x;
+        float p1 = acc[j][1] * t_lo[j].y + acc[j][3] * t_hi[j].y;
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
           p0 += __shfl_xor_sync(0xffffffffu, p0, o);
@@ -185,30 +191,54 @@ rows_kernel(const RowsArgs a) {
           atomicAdd(&red[s * RP + col + 1], p1);
         }
       }
-      if (ok_lo) emit(a.U + static_cast<size_t>(r_lo) * a.ldu, col, d0, d1);
-      if (ok_hi) emit(a.U + static_cast<size_t>(r_hi) * a.ldu, col, d2, d3);
+    }
+  }
+  cp_async_wait<0>();
+
+  if (a.mode != 0) {
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      const int col = j * 8 + 2 * t;
+      if (ok_lo) emit(a.U + static_cast<size_t>(r_lo) * a.ldu, col, d[j][0], d[j][1]);
+      if (ok_hi) emit(a.U + static_cast<size_t>(r_hi) * a.ldu, col, d[j][2], d[j][3]);
     }
     __syncthreads();
     for (int i = tid; i < CS * RP; i += 256) atomicAdd(a.dc + i, red[i]);
   }
 }
 
+static int rows_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int RT, int CS>
-static int rows_launch_t(const RowsArgs& a, cudaStream_t st) {
+static int rows_launch_t(RowsArgs a, int num_sms, cudaStream_t st) {
   constexpr int smem = R_STAGES * (R_BM * R_BK * 2 + 2 * RT * 8 * R_BK * 2);
   static bool done = false;
   if (!done) {
     if (cudaFuncSetAttribute(rows_kernel<RT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -31;
     done = true;
   }
-  rows_kernel<RT, CS><<<(a.M + R_BM - 1) / R_BM, 256, smem, st>>>(a);
+  // the smallest whole number of CTA "layers" (one CTA on every SM) whose even row share fits a 128-row CTA
+  if (num_sms <= 0) num_sms = rows_sm_count();
+  int layers = (a.M + num_sms * R_BM - 1) / (num_sms * R_BM);
+  int grid = layers * num_sms;
+  a.rows_per_cta = (a.M + grid - 1) / grid;
+  grid = (a.M + a.rows_per_cta - 1) / a.rows_per_cta;
+  rows_kernel<RT, CS><<<grid, 256, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -32;
 }
 
-int rows_launch(const RowsArgs& a, int rp, int cs, cudaStream_t st) {
+int rows_launch(const RowsArgs& a, int rp, int cs, int num_sms, cudaStream_t st) {
   if (a.M <= 0 || a.kslice % R_BK != 0 || (rp != 16 && rp != 32)) return -30;
   if (a.mode == 0 && cs != 1) return -30;
-#define CARA_ROWS(RT, CS) if (rp == RT * 8 && cs == CS) return rows_launch_t<RT, CS>(a, st);
+#define CARA_ROWS(RT, CS) if (rp == RT * 8 && cs == CS) return rows_launch_t<RT, CS>(a, num_sms, st);
   CARA_ROWS(2, 1) CARA_ROWS(2, 3) CARA_ROWS(2, 4) CARA_ROWS(4, 1) CARA_ROWS(4, 3) CARA_ROWS(4, 4)
 #undef CARA_ROWS
   return -30;
@@ -328,8 +358,13 @@ static int cols_launch_t(ColsArgs a, int num_sms, cudaStream_t st) {
     if (cudaFuncSetAttribute(cols_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -41;
     done = true;
   }
+  // Exactly `mult` CTAs per SM or fewer, never one more: every SM streams at the same rate, so an SM that gets an
+  // extra CTA finishes (mult+1)/mult later and the whole HBM-bound launch waits for it (ncu: 34 % SM-idle at 300 CTAs).
   const int ksplits = a.Kc / C_BK;
-  int msplits = (2 * num_sms + ksplits - 1) / ksplits;
+  static int mult = -1;
+  if (mult < 0) { const char* e = getenv("CARA_COLS_MULT"); mult = (e != nullptr && atoi(e) > 0) ? atoi(e) : 2; }
+  int msplits = (mult * num_sms) / ksplits;
+  if (msplits < 1) msplits = 1;
   int rows = (a.M + msplits - 1) / msplits;
   rows = ((rows + C_BM - 1) / C_BM) * C_BM;
   msplits = (a.M + rows - 1) / rows;
