@@ -63,6 +63,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                                                  // nothing above touches global memory
+  pdl_trigger();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -214,6 +216,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o,
                   const __nv_bfloat16* __restrict__ o_lo, float* __restrict__ delta, int rows, int N, int H) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int b = row / N, n = row % N;
@@ -324,6 +328,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                                                  // nothing above touches global memory
+  pdl_trigger();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -604,8 +610,7 @@ int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
       return -52;
     configured = true;
   }
-  attn_fwd_tc_kernel<<<a.B * a.H, TC_THREADS, smem, st>>>(map, a, npad);
-  return cudaGetLastError() == cudaSuccess ? 0 : -53;
+  return launch_pdl(attn_fwd_tc_kernel, dim3(a.B * a.H), dim3(TC_THREADS), smem, st, map, a, npad) == cudaSuccess ? 0 : -53;
 }
 
 }  // namespace cara
@@ -632,10 +637,11 @@ int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
   }
   int grid = a.B * a.H;
   if (grid > 148) grid = 148;
-  attn_delta_kernel<<<static_cast<int>((rows + 7) / 8), 256, 0, st>>>(a.d_o, a.o, a.o_lo, a.delta, static_cast<int>(rows),
-                                                                     a.N, a.H);
-  attn_bwd_tc_kernel<<<grid, TCB_THREADS, smem, st>>>(map_qkv, map_do, a, npad, qk_pairs);
-  return cudaGetLastError() == cudaSuccess ? 0 : -53;
+  if (launch_pdl(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, a.d_o, a.o, a.o_lo, a.delta,
+                 static_cast<int>(rows), a.N, a.H) != cudaSuccess)
+    return -53;
+  return launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(TCB_THREADS), smem, st, map_qkv, map_do, a, npad, qk_pairs) ==
+                 cudaSuccess ? 0 : -53;
 }
 int attn_debug_read(long long* out, int n) {
   if (n > 64) n = 64;

@@ -21,6 +21,7 @@
 // with plain 16-byte loads: one full 128-byte line per thread and step.
 #include "ptx.cuh"
 #include "gemm_sm100.h"
+#include "kernels.h"
 #include "mathfn.cuh"
 
 #include <stdlib.h>
@@ -128,6 +129,8 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers + TMEM visible (to the peer CTA as well)
+  pdl_wait();                                              // nothing above touches global memory
+  pdl_trigger();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -377,13 +380,15 @@ static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& b0, cons
   cfg.blockDim = dim3(num_threads(EPI));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_cp_kernel<EPI, PAIR>, a0, b0, a1, b1, mo, mx, args);
 }
 

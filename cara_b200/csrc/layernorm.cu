@@ -49,6 +49,8 @@ ln_fwd_kernel(const float* __restrict__ x_in, const ActT* __restrict__ delta, co
               const float* __restrict__ beta, ActT* __restrict__ h, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, float eps) {
   constexpr int C = NV * 128;
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -101,6 +103,8 @@ ln_bwd_kernel(const ActT* __restrict__ dh, const float* __restrict__ x, const fl
               float* __restrict__ dx_out, ActT* __restrict__ g_out, const float* __restrict__ rowscale,
               int rows_per_sample, int M) {
   constexpr int C = NV * 128;
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -137,35 +141,37 @@ ln_bwd_kernel(const ActT* __restrict__ dh, const float* __restrict__ x, const fl
 template <typename ActT>
 static int ln_fwd_t(const LnFwdArgs& a, cudaStream_t st) {
   const int grid = (a.M + 7) / 8;
+  cudaError_t err = cudaSuccess;
 #define CARA_LN_FWD(NV)                                                                                       \
   case NV:                                                                                                    \
-    ln_fwd_kernel<NV, ActT><<<grid, 256, 0, st>>>(a.x_in, static_cast<const ActT*>(a.delta), a.rowscale,      \
-                                                   a.rows_per_sample, a.x_out, a.gamma, a.beta,               \
-                                                   static_cast<ActT*>(a.h), a.mean, a.rstd, a.M, a.eps);      \
+    err = launch_pdl(ln_fwd_kernel<NV, ActT>, dim3(grid), dim3(256), 0, st, a.x_in,                           \
+                     static_cast<const ActT*>(a.delta), a.rowscale, a.rows_per_sample, a.x_out, a.gamma, a.beta, \
+                     static_cast<ActT*>(a.h), a.mean, a.rstd, a.M, a.eps);                                    \
     break;
   switch (a.C / 128) {
     CARA_LN_FWD(1) CARA_LN_FWD(2) CARA_LN_FWD(3) CARA_LN_FWD(4) CARA_LN_FWD(6) CARA_LN_FWD(8) CARA_LN_FWD(10)
     default: return -20;
   }
 #undef CARA_LN_FWD
-  return cudaGetLastError() == cudaSuccess ? 0 : -21;
+  return err == cudaSuccess ? 0 : -21;
 }
 
 template <typename ActT>
 static int ln_bwd_t(const LnBwdArgs& a, cudaStream_t st) {
   const int grid = (a.M + 7) / 8;
+  cudaError_t err = cudaSuccess;
 #define CARA_LN_BWD(NV)                                                                                       \
   case NV:                                                                                                    \
-    ln_bwd_kernel<NV, ActT><<<grid, 256, 0, st>>>(static_cast<const ActT*>(a.dh), a.x, a.mean, a.rstd,        \
-                                                   a.gamma, a.dx_in, a.dx_out, static_cast<ActT*>(a.g_out),   \
-                                                   a.rowscale, a.rows_per_sample, a.M);                       \
+    err = launch_pdl(ln_bwd_kernel<NV, ActT>, dim3(grid), dim3(256), 0, st, static_cast<const ActT*>(a.dh),   \
+                     a.x, a.mean, a.rstd, a.gamma, a.dx_in, a.dx_out, static_cast<ActT*>(a.g_out), a.rowscale, \
+                     a.rows_per_sample, a.M);                                                                 \
     break;
   switch (a.C / 128) {
     CARA_LN_BWD(1) CARA_LN_BWD(2) CARA_LN_BWD(3) CARA_LN_BWD(4) CARA_LN_BWD(6) CARA_LN_BWD(8) CARA_LN_BWD(10)
     default: return -20;
   }
 #undef CARA_LN_BWD
-  return cudaGetLastError() == cudaSuccess ? 0 : -21;
+  return err == cudaSuccess ? 0 : -21;
 }
 
 int ln_fwd_launch(const LnFwdArgs& a, cudaStream_t st) {

@@ -40,6 +40,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 // (the scalar kernel above visited every 128-byte line 16 times: 293 us at batch 256 against a 36 us HBM floor).
 __global__ void __launch_bounds__(256)
 patchify16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long total, int Cin, int S, int Kp) {
+  pdl_wait();
+  pdl_trigger();
   const int gp = S / 16;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -66,6 +68,8 @@ patchify16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out
 // x[b, 0, :] = cls + pos[0];  x[b, 1+p, :] = pe[b*np + p, :] + pos[1+p]   (fp32 residual stream)
 __global__ void assemble_kernel(const __nv_bfloat16* __restrict__ pe, const float* __restrict__ cls,
                                 const float* __restrict__ pos, float* __restrict__ x, int B, int N, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long total = static_cast<long>(B) * N * (C / 4);
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -91,8 +95,7 @@ int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S,
   if (S % P != 0 || Kp < Cin * P * P) return -60;
   if (P == 16 && Kp == Cin * 256 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const long total = static_cast<long>(B) * Cin * S * (S / 16);
-    patchify16_kernel<<<148 * 16, 256, 0, st>>>(img, out, total, Cin, S, Kp);
-    return cudaGetLastError() == cudaSuccess ? 0 : -61;
+    return launch_pdl(patchify16_kernel, dim3(148 * 16), dim3(256), 0, st, img, out, total, Cin, S, Kp) == cudaSuccess ? 0 : -61;
   }
   patchify_kernel<<<148 * 8, 256, 0, st>>>(img, out, B, Cin, S, P, Kp);
   return cudaGetLastError() == cudaSuccess ? 0 : -61;
@@ -100,8 +103,7 @@ int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S,
 int assemble_launch(const __nv_bfloat16* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
                     cudaStream_t st) {
   if (C % 4 != 0) return -62;
-  assemble_kernel<<<148 * 8, 256, 0, st>>>(pe, cls, pos, x, B, N, C);
-  return cudaGetLastError() == cudaSuccess ? 0 : -63;
+  return launch_pdl(assemble_kernel, dim3(148 * 8), dim3(256), 0, st, pe, cls, pos, x, B, N, C) == cudaSuccess ? 0 : -63;
 }
 
 // ---------------------------------------------------------------- eval-mode merge

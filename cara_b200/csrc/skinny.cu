@@ -66,6 +66,8 @@ rows_kernel(const RowsArgs a) {
   constexpr int ST_BYTES = XS_BYTES + FS_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float red[CS * RP];
+  pdl_wait();
+  pdl_trigger();
   const uint32_t sbase = s_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * a.rows_per_cta;
@@ -231,8 +233,7 @@ static int rows_launch_t(RowsArgs a, int num_sms, cudaStream_t st) {
   int grid = layers * num_sms;
   a.rows_per_cta = (a.M + grid - 1) / grid;
   grid = (a.M + a.rows_per_cta - 1) / a.rows_per_cta;
-  rows_kernel<RT, CS><<<grid, 256, smem, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : -32;
+  return launch_pdl(rows_kernel<RT, CS>, dim3(grid), dim3(256), smem, st, a) == cudaSuccess ? 0 : -32;
 }
 
 int rows_launch(const RowsArgs& a, int rp, int cs, int num_sms, cudaStream_t st) {
@@ -257,6 +258,8 @@ cols_kernel(const ColsArgs a) {
   constexpr int VS_BYTES = C_BM * VSTR;
   constexpr int ST_BYTES = XS_BYTES + ((VS_BYTES + 127) / 128) * 128;
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_wait();
+  pdl_trigger();
   const uint32_t sbase = s_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * C_BK;
@@ -369,8 +372,7 @@ static int cols_launch_t(ColsArgs a, int num_sms, cudaStream_t st) {
   rows = ((rows + C_BM - 1) / C_BM) * C_BM;
   msplits = (a.M + rows - 1) / rows;
   a.rows_per_cta = rows;
-  cols_kernel<RT><<<dim3(ksplits, msplits), 256, smem, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : -42;
+  return launch_pdl(cols_kernel<RT>, dim3(ksplits, msplits), dim3(256), smem, st, a) == cudaSuccess ? 0 : -42;
 }
 
 int cols_launch(const ColsArgs& a, int rp, int num_sms, cudaStream_t st) {
