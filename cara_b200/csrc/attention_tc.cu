@@ -610,7 +610,7 @@ int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
       return -52;
     configured = true;
   }
-  return launch_pdl(attn_fwd_tc_kernel, dim3(a.B * a.H), dim3(TC_THREADS), smem, st, map, a, npad) == cudaSuccess ? 0 : -53;
+  return launch_pdl_f<2>(attn_fwd_tc_kernel, dim3(a.B * a.H), dim3(TC_THREADS), smem, st, map, a, npad) == cudaSuccess ? 0 : -53;
 }
 
 }  // namespace cara
@@ -637,10 +637,10 @@ int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
   }
   int grid = a.B * a.H;
   if (grid > 148) grid = 148;
-  if (launch_pdl(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, a.d_o, a.o, a.o_lo, a.delta,
+  if (launch_pdl_f<2>(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, a.d_o, a.o, a.o_lo, a.delta,
                  static_cast<int>(rows), a.N, a.H) != cudaSuccess)
     return -53;
-  return launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(TCB_THREADS), smem, st, map_qkv, map_do, a, npad, qk_pairs) ==
+  return launch_pdl_f<2>(attn_bwd_tc_kernel, dim3(grid), dim3(TCB_THREADS), smem, st, map_qkv, map_do, a, npad, qk_pairs) ==
                  cudaSuccess ? 0 : -53;
 }
 int attn_debug_read(long long* out, int n) {

@@ -388,7 +388,7 @@ static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& b0, cons
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = (pdl_mask() & 1) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_cp_kernel<EPI, PAIR>, a0, b0, a1, b1, mo, mx, args);
 }
 

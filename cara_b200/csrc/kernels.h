@@ -23,6 +23,26 @@ inline bool pdl_enabled() {
   if (on < 0) { const char* e = getenv("CARA_PDL"); on = (e != nullptr && e[0] == '1') ? 1 : 0; }
   return on == 1;
 }
+// pdl_mask bit per kernel family (CARA_PDL is a bit mask: 1 GEMM, 2 attention, 4 LayerNorm, 8 rows/cols, 16 small)
+inline int pdl_mask() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("CARA_PDL"); m = e != nullptr ? atoi(e) : 0; }
+  return m;
+}
+template <int FAMILY, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_f(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & FAMILY) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};

@@ -144,7 +144,7 @@ static int ln_fwd_t(const LnFwdArgs& a, cudaStream_t st) {
   cudaError_t err = cudaSuccess;
 #define CARA_LN_FWD(NV)                                                                                       \
   case NV:                                                                                                    \
-    err = launch_pdl(ln_fwd_kernel<NV, ActT>, dim3(grid), dim3(256), 0, st, a.x_in,                           \
+    err = launch_pdl_f<4>(ln_fwd_kernel<NV, ActT>, dim3(grid), dim3(256), 0, st, a.x_in,                           \
                      static_cast<const ActT*>(a.delta), a.rowscale, a.rows_per_sample, a.x_out, a.gamma, a.beta, \
                      static_cast<ActT*>(a.h), a.mean, a.rstd, a.M, a.eps);                                    \
     break;
@@ -162,7 +162,7 @@ static int ln_bwd_t(const LnBwdArgs& a, cudaStream_t st) {
   cudaError_t err = cudaSuccess;
 #define CARA_LN_BWD(NV)                                                                                       \
   case NV:                                                                                                    \
-    err = launch_pdl(ln_bwd_kernel<NV, ActT>, dim3(grid), dim3(256), 0, st, static_cast<const ActT*>(a.dh),   \
+    err = launch_pdl_f<4>(ln_bwd_kernel<NV, ActT>, dim3(grid), dim3(256), 0, st, static_cast<const ActT*>(a.dh),   \
                      a.x, a.mean, a.rstd, a.gamma, a.dx_in, a.dx_out, static_cast<ActT*>(a.g_out), a.rowscale, \
                      a.rows_per_sample, a.M);                                                                 \
     break;

@@ -95,7 +95,7 @@ int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S,
   if (S % P != 0 || Kp < Cin * P * P) return -60;
   if (P == 16 && Kp == Cin * 256 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const long total = static_cast<long>(B) * Cin * S * (S / 16);
-    return launch_pdl(patchify16_kernel, dim3(148 * 16), dim3(256), 0, st, img, out, total, Cin, S, Kp) == cudaSuccess ? 0 : -61;
+    return launch_pdl_f<16>(patchify16_kernel, dim3(148 * 16), dim3(256), 0, st, img, out, total, Cin, S, Kp) == cudaSuccess ? 0 : -61;
   }
   patchify_kernel<<<148 * 8, 256, 0, st>>>(img, out, B, Cin, S, P, Kp);
   return cudaGetLastError() == cudaSuccess ? 0 : -61;
@@ -103,7 +103,7 @@ int patchify_launch(const float* img, __nv_bfloat16* out, int B, int Cin, int S,
 int assemble_launch(const __nv_bfloat16* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
                     cudaStream_t st) {
   if (C % 4 != 0) return -62;
-  return launch_pdl(assemble_kernel, dim3(148 * 8), dim3(256), 0, st, pe, cls, pos, x, B, N, C) == cudaSuccess ? 0 : -63;
+  return launch_pdl_f<16>(assemble_kernel, dim3(148 * 8), dim3(256), 0, st, pe, cls, pos, x, B, N, C) == cudaSuccess ? 0 : -63;
 }
 
 // ---------------------------------------------------------------- eval-mode merge

@@ -233,7 +233,7 @@ static int rows_launch_t(RowsArgs a, int num_sms, cudaStream_t st) {
   int grid = layers * num_sms;
   a.rows_per_cta = (a.M + grid - 1) / grid;
   grid = (a.M + a.rows_per_cta - 1) / a.rows_per_cta;
-  return launch_pdl(rows_kernel<RT, CS>, dim3(grid), dim3(256), smem, st, a) == cudaSuccess ? 0 : -32;
+  return launch_pdl_f<8>(rows_kernel<RT, CS>, dim3(grid), dim3(256), smem, st, a) == cudaSuccess ? 0 : -32;
 }
 
 int rows_launch(const RowsArgs& a, int rp, int cs, int num_sms, cudaStream_t st) {
@@ -372,7 +372,7 @@ static int cols_launch_t(ColsArgs a, int num_sms, cudaStream_t st) {
   rows = ((rows + C_BM - 1) / C_BM) * C_BM;
   msplits = (a.M + rows - 1) / rows;
   a.rows_per_cta = rows;
-  return launch_pdl(cols_kernel<RT>, dim3(ksplits, msplits), dim3(256), smem, st, a) == cudaSuccess ? 0 : -42;
+  return launch_pdl_f<8>(cols_kernel<RT>, dim3(ksplits, msplits), dim3(256), smem, st, a) == cudaSuccess ? 0 : -42;
 }
 
 int cols_launch(const ColsArgs& a, int rp, int num_sms, cudaStream_t st) {
