@@ -45,6 +45,8 @@ _SIGS = {
     "cara_debug_read": (C.c_int, [_P, C.c_int]),
     "cara_gelu_f32": (C.c_int, [_P, _P, _P, C.c_long, _P]),
     "cara_attn_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "cara_resize_normalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P,
+                                        C.c_int, C.c_int, _P, _P, _P]),
     "cara_patchify": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cara_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "cara_merge_weights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -113,6 +113,13 @@ int cara_attn_f32(const float* qkv, float* o, float* lse, const float* d_o, floa
   CARA_RET(cara::attn_f32_launch(qkv, o, lse, d_o, dqkv, B, N, H, D, scale, CARA_STREAM(stream)), "cara_attn_f32");
 }
 int cara_debug_read(long long* out, int n) { return cara::attn_debug_read(out, n); }
+int cara_resize_normalize(const unsigned char* src, int B, int H, int W, const int* xbounds, const int* xk, int xksize,
+                          const int* ybounds, const int* yk, int yksize, unsigned char* tmp, float* out,
+                          unsigned char* out_u8, int OH, int OW, const float* mean3, const float* std3, void* stream) {
+  if (mean3 == nullptr || std3 == nullptr) return fail(-80, "cara_resize_normalize: mean3 / std3 are host pointers to 3 floats");
+  CARA_RET(cara::resize_norm_launch(src, B, H, W, xbounds, xk, xksize, ybounds, yk, yksize, tmp, out, out_u8, OH, OW, mean3,
+                                    std3, CARA_STREAM(stream)), "cara_resize_normalize");
+}
 int cara_patchify(const float* img, void* patches, int B, int Cin, int S, int P, int Kp, void* stream) {
   CARA_RET(cara::patchify_launch(img, static_cast<bf16*>(patches), B, Cin, S, P, Kp, CARA_STREAM(stream)), "cara_patchify");
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include <stdlib.h>
 #include <utility>
@@ -124,5 +125,10 @@ int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr,
                  float wd, int step, float gscale, cudaStream_t st);
 int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
                  const float* bias, int M, int N, int K, float alpha, float beta, cudaStream_t st);
+
+// GPU input pipeline (preprocess.cu): Pillow-exact bicubic Resize + ToTensor + Normalize on uint8 HWC images
+int resize_norm_launch(const uint8_t* src, int B, int H, int W, const int* xbounds, const int* xk, int xksize,
+                       const int* ybounds, const int* yk, int yksize, uint8_t* tmp, float* out, uint8_t* out_u8,
+                       int OH, int OW, const float* mean, const float* stdv, cudaStream_t st);
 
 }  // namespace cara

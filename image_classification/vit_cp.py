@@ -21,7 +21,7 @@ import numpy as np
 import torch as th
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from vtab import get_classes_num, get_data  # noqa: E402
+from vtab import get_classes_num, get_data, to_device  # noqa: E402
 from vtab_config import config  # noqa: E402
 
 from cara_b200 import train as T  # noqa: E402
@@ -36,7 +36,7 @@ def test(model, dl):
     model.eval()
     correct = total = 0
     for x, y in dl:
-        x, y = x.cuda(non_blocking=True), y.cuda(non_blocking=True)
+        x, y = to_device(x, y)
         correct += int((model(x).argmax(dim=1).view(-1) == y).sum())
         total += int(y.numel())
     return correct / max(total, 1)
@@ -48,7 +48,7 @@ def train(args, model, dl, tdl, opt, epochs, world_size=1, rank=0):
     acc, old_name, use_sched = 0.0, None, True
     for epoch in range(epochs):
         for x, y in dl:
-            x, y = x.cuda(non_blocking=True), y.cuda(non_blocking=True)
+            x, y = to_device(x, y)
             if world_size > 1:
                 lo, hi = T.shard_batch(x.shape[0], rank, world_size)
                 x, y = x[lo:hi], y[lo:hi]
@@ -82,6 +82,8 @@ def _parse_args():
     p.add_argument("--batch-size", type=int, default=64, help="global train batch")
     p.add_argument("--synthetic", action="store_true", help="force VTAB-shaped synthetic data")
     p.add_argument("--no-merge", action="store_true", help="evaluate without folding the CP delta into W")
+    p.add_argument("--gpu-preprocess", action="store_true",
+                   help="decode on the CPU, resize + normalise on the GPU (bit-identical to the reference's transforms)")
     return p.parse_args()
 
 
@@ -106,7 +108,7 @@ def main(sd=None):
     th.cuda.manual_seed_all(seed)
 
     train_dl, test_dl = get_data(name, evaluate=True, batch_size=args.batch_size,
-                                 synthetic=True if args.synthetic else None)
+                                 synthetic=True if args.synthetic else None, gpu_preprocess=args.gpu_preprocess)
     num_classes = get_classes_num(name)
     vit = create_model(args.model, checkpoint_path="./ViT-B_16.npz", drop_path_rate=0.1)
     vit = cara({"model": vit, "rank": args.dim, "scale": scale, "l_mu": data_config["init_mean"],

@@ -5,7 +5,9 @@ class counts (reference vtab.py:9-34) and ``get_data``.  When ``./data/vtab-1k/<
 the benchmark boxes, which have no datasets -- ``get_data`` returns synthetic loaders with the reference's
 shapes (x ~ N(0,1) [B,3,224,224] as after Normalize, labels uniform over the classes; train batch 64 with
 drop_last over 1000 images, val batch 256).  The real-file path (PIL decode, bicubic 224, ImageNet
-normalise) is kept minimal; a GPU input pipeline is listed as next work in DESIGN.md.
+normalise) follows the reference; with ``gpu_preprocess=True`` the workers only decode (uint8 HWC) and
+``cara_b200.preprocess.GpuPreprocessor`` does the bit-identical resize + ToTensor + Normalize on the GPU
+(``to_device(batch)`` turns either kind of batch into the model's input).
 """
 import os
 
@@ -38,9 +40,10 @@ class SyntheticImages(torch.utils.data.Dataset):
 
 
 class _FileList(torch.utils.data.Dataset):
-    def __init__(self, root, flist):
+    def __init__(self, root, flist, decode_only=False):
         from torchvision import transforms
         self.root = root
+        self.decode_only = decode_only
         with open(flist) as f:
             self.items = [(p, int(lab)) for p, lab in (ln.split() for ln in f if ln.strip())]
         self.tf = transforms.Compose([
@@ -54,10 +57,37 @@ class _FileList(torch.utils.data.Dataset):
     def __getitem__(self, i):
         from PIL import Image
         path, lab = self.items[i]
-        return self.tf(Image.open(os.path.join(self.root, path)).convert("RGB")), lab
+        img = Image.open(os.path.join(self.root, path)).convert("RGB")
+        if self.decode_only:
+            import numpy as np
+            return np.asarray(img), lab
+        return self.tf(img), lab
 
 
-def get_data(name, evaluate=True, batch_size=64, synthetic=None, train_len=1000, val_len=512):
+def _collate_decoded(batch):
+    """Decoded images keep their own sizes: a list of uint8 [H,W,3] arrays + the label tensor."""
+    return [b[0] for b in batch], torch.as_tensor([b[1] for b in batch])
+
+
+_PRE = {}
+
+
+def to_device(x, y, device="cuda"):
+    """A loader batch -> (fp32 [B,3,224,224], labels) on the device; decoded uint8 batches go through the GPU
+    resize / normalise kernels."""
+    if isinstance(x, (list, tuple)):
+        from cara_b200.preprocess import GpuPreprocessor
+        dev = torch.device(device)
+        if dev.index is None and dev.type == "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        pre = _PRE.get(dev)
+        if pre is None:
+            pre = _PRE[dev] = GpuPreprocessor(dev)
+        return pre(x), y.to(dev, non_blocking=True)
+    return x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+
+
+def get_data(name, evaluate=True, batch_size=64, synthetic=None, train_len=1000, val_len=512, gpu_preprocess=False):
     root = "./data/vtab-1k/" + name
     if synthetic is None:
         synthetic = not os.path.isdir(root)
@@ -69,10 +99,11 @@ def get_data(name, evaluate=True, batch_size=64, synthetic=None, train_len=1000,
     else:
         print(f"Getting data from root: {root}")
         tr, va = ("/train800val200.txt", "/test.txt") if evaluate else ("/train800.txt", "/val200.txt")
-        train, val = _FileList(root, root + tr), _FileList(root, root + va)
+        train, val = _FileList(root, root + tr, gpu_preprocess), _FileList(root, root + va, gpu_preprocess)
         workers = 4
+    collate = _collate_decoded if (gpu_preprocess and not synthetic) else None
     train_loader = torch.utils.data.DataLoader(train, batch_size=batch_size, shuffle=True, drop_last=True,
-                                               num_workers=workers, pin_memory=True)
+                                               num_workers=workers, pin_memory=collate is None, collate_fn=collate)
     val_loader = torch.utils.data.DataLoader(val, batch_size=256, shuffle=False, num_workers=workers,
-                                             pin_memory=True)
+                                             pin_memory=collate is None, collate_fn=collate)
     return train_loader, val_loader

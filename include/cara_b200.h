@@ -114,6 +114,19 @@ CARA_API int cara_gelu_f32(const float* dy, const float* x, float* out, long n, 
 CARA_API int cara_attn_f32(const float* qkv, float* o, float* lse, const float* d_o, float* dqkv, int B, int N, int H,
                            int D, float scale, void* stream);
 
+/* Input pipeline of the entry point (reference image_classification/vtab.py:79-82):
+ *   transforms.Resize((OH, OW), interpolation=3) -> ToTensor() -> Normalize(mean3, std3)
+ * on B decoded uint8 images src [B,H,W,3] (device).  The resize is Pillow's two-pass antialiased bicubic, bit-exact:
+ * xbounds/xk (ybounds/yk) are Pillow's integer tap tables for W -> OW (H -> OH): bounds [O,2] = (first tap, taps),
+ * k [O, ksize] = 22-bit fixed-point coefficients (cara_b200/preprocess.py builds them; device pointers); pass NULL
+ * tables for a dimension that already has the output size.  tmp [B,H,OW,3] uint8 is scratch for the horizontal pass;
+ * out [B,3,OH,OW] fp32 and/or out_u8 [B,OH,OW,3] (the resized image before ToTensor) may be NULL.
+ * mean3 / std3 are HOST pointers. */
+CARA_API int cara_resize_normalize(const unsigned char* src, int B, int H, int W, const int* xbounds, const int* xk,
+                                   int xksize, const int* ybounds, const int* yk, int yksize, unsigned char* tmp,
+                                   float* out, unsigned char* out_u8, int OH, int OW, const float* mean3,
+                                   const float* std3, void* stream);
+
 /* timm PatchEmbed (conv PxP stride P) as im2col: img fp32 [B,Cin,S,S] -> bf16 [B*(S/P)^2, Kp] (zero padded),
  * then cara_gemm_cp against the flattened conv weight, then token assembly with cls/pos into the fp32
  * residual stream x [B,N,C]. */
