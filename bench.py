@@ -108,6 +108,11 @@ def build_model(cfg, device):
     return vit, opt
 
 
+def apply_weight_dropout(vit, mode):
+    from cara_b200 import wdrop
+    wdrop.set_weight_dropout(vit, mode)
+
+
 def _install_init_module():
     """Random-init weights of the architecture + non-default CP factors (the reference's default init makes every
     delta exactly zero, cara.py:128,132; SURVEY D.3 recipe keeps the adapter numerically alive)."""
@@ -153,6 +158,7 @@ def run_cuda(args):
     cfg = CONFIGS[args.config]
     B = args.batch or cfg["batch"]
     vit, opt = build_model(cfg, dev)
+    apply_weight_dropout(vit, args.weight_dropout)
     if cfg.get("eval"):
         return run_eval(args, cfg, vit, dev, world, rank)
     img = 224
@@ -264,7 +270,9 @@ def run_cuda(args):
                    if args.config == "vitb16_r16" else args.config,
                    "config_key": args.config, "batch_per_gpu": B, "global_batch": B * world, "tokens": 197,
                    "parallelism": "dp%d" % world, "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2",
-                   "drop_path": 0.1, "weight_dropout": "not applied (documented deviation)",
+                   "drop_path": 0.1,
+                   "weight_dropout": "not applied (documented deviation; --weight-dropout exact selects the slow path)"
+                   if args.weight_dropout == "skip" else "exact (reference semantics: 3 GEMMs per projection)",
                    "cuda_graph": not args.no_graph,
                    "algorithmic_gflop_per_image": cfg["gflop_per_image"]},
         "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/s",
@@ -414,6 +422,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weight-dropout", default="skip", choices=["skip", "exact"],
+                    help="exact: the reference's nn.Dropout(0.1) on the materialised delta weights (slow path)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

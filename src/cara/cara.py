@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from cara_b200 import staging as _staging
 from cara_b200 import vit as _vit
+from cara_b200 import wdrop as _wdrop
 
 global_model: th.nn.Module
 
@@ -32,7 +33,8 @@ def _weight_dropout_note(mod):
     if mod.training and mod.dp.p > 0.0 and not _warned[0]:
         _warned[0] = True
         warnings.warn("cara_b200: weight-space dropout on the CP delta (reference cara.py:35,57,81,92) is not "
-                      "applied by the fused kernels; training proceeds without it")
+                      "applied by the fused kernels; training proceeds without it "
+                      "(cara_b200.wdrop.set_weight_dropout(model, 'exact') selects the exact slow path)")
 
 
 def cp_attn(self, x: th.Tensor) -> th.Tensor:
@@ -44,8 +46,10 @@ def cp_attn(self, x: th.Tensor) -> th.Tensor:
     Returns:
         th.Tensor: CaRA attention output [B, N, C].
     """
-    _weight_dropout_note(self)
     amap, _ = _staging.staged(global_model)
+    if _wdrop.wants_exact(global_model, self):     # opt-in slow path: the reference's dropout on the delta weights
+        return _wdrop.attn_forward(self, x, amap[id(self)])
+    _weight_dropout_note(self)
     return _vit.attn_forward(self, x, amap[id(self)])
 
 
@@ -58,8 +62,10 @@ def cp_mlp(self, x: th.Tensor) -> th.Tensor:
     Returns:
         th.Tensor: Mlp projected output [B, N, C].
     """
-    _weight_dropout_note(self)
     _, mmap = _staging.staged(global_model)
+    if _wdrop.wants_exact(global_model, self):
+        return _wdrop.mlp_forward(self, x, mmap[id(self)])
+    _weight_dropout_note(self)
     return _vit.mlp_forward(self, x, mmap[id(self)])
 
 

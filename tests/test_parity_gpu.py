@@ -232,3 +232,41 @@ def test_fp32_mode_vs_fp64_oracle_reduced_depth():
     assert rel(logits, o_logits) <= 1e-4
     for k in o_grads:
         assert rel(grads[k], o_grads[k]) <= 1e-3, (k, rel(grads[k], o_grads[k]))
+
+
+def test_exact_weight_dropout_mode_replays_through_oracle(monkeypatch):
+    """cara.py:35,57,81,92: nn.Dropout(0.1) on the materialised delta weights in train mode.  The opt-in exact mode
+    (cara_b200.wdrop) draws its masks on the GPU; replay the very same masks through the oracle's dropout calls
+    (qkv [3,C,C] as [slice,in,out], proj / fc1 transposed, fc2 as is) and compare logits, loss and every gradient."""
+    from cara_b200 import wdrop
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    vit, st = build(g, 1.0)
+    wdrop.set_weight_dropout(vit, "exact")
+    vit.train()
+    torch.manual_seed(11)
+    torch.cuda.manual_seed_all(11)
+    taps = []
+    monkeypatch.setattr(wdrop, "MASK_TAP", taps)
+    x, y = O.synthetic_batch(g, 3)
+    logits, loss, grads = run_step(vit, x, y)
+    assert len(taps) == 4 * g.depth and all(float((m == 0).float().mean()) > 0.05 for m in taps)
+    C = g.embed_dim
+    queue = []
+    for l in range(g.depth):
+        q, p, u, d = [m.cpu() for m in taps[4 * l:4 * l + 4]]
+        queue += [q.view(3, C, C).transpose(1, 2), p.t(), u.t(), d.t()]      # the layouts the oracle drops out in
+
+    def replay(t, p_, train):
+        if not train:
+            return t
+        m = queue.pop(0)
+        assert m.shape == t.shape, (m.shape, t.shape)
+        return t * m.to(t.dtype)
+    monkeypatch.setattr(O, "_wdrop", replay)
+    o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, 1.0, train=True, wdrop=0.1)
+    assert not queue
+    # a two-block model has few terms for the bf16 roundings to average over (see test_reduced_depth_geometries)
+    check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, "exact weight dropout", logits_tol=1.5e-2)
+    # and the masks matter: the same step without them is measurably different
+    n_logits, _, _ = O.loss_and_grads(st, g, x, y, 1.0)
+    assert rel(n_logits, o_logits) > 3 * rel(logits, o_logits)
