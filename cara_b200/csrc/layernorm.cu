@@ -110,8 +110,14 @@ ln_bwd_kernel(const ActT* __restrict__ dh, const float* __restrict__ x, const fl
   if (row >= M) return;
   const size_t base = static_cast<size_t>(row) * C;
   const float mean = mean_in[row], rstd = rstd_in[row];
-  float4 dy[NV], xh[NV];
+  float4 dy[NV], xh[NV], rin[NV];
   float s1 = 0.f, s2 = 0.f;
+  // the incoming residual gradient is requested together with dh and x (one memory round trip per row, not two:
+  // it is only needed after the two warp reductions)
+  if (dx_in != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) rin[i] = load4(dx_in + base + (i * 32 + lane) * 4);
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c0 = (i * 32 + lane) * 4;
@@ -129,10 +135,7 @@ ln_bwd_kernel(const ActT* __restrict__ dh, const float* __restrict__ x, const fl
     float4 o;
     o.x = rstd * (dy[i].x - m1 - xh[i].x * m2); o.y = rstd * (dy[i].y - m1 - xh[i].y * m2);
     o.z = rstd * (dy[i].z - m1 - xh[i].z * m2); o.w = rstd * (dy[i].w - m1 - xh[i].w * m2);
-    if (dx_in != nullptr) {
-      const float4 r = load4(dx_in + base + c0);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-    }
+    if (dx_in != nullptr) { o.x += rin[i].x; o.y += rin[i].y; o.z += rin[i].z; o.w += rin[i].w; }
     store4(dx_out + base + c0, o);
     if (g_out != nullptr) store4(g_out + base + c0, make_float4(o.x * rs, o.y * rs, o.z * rs, o.w * rs));
   }
