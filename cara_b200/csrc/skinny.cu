@@ -339,10 +339,11 @@ cols_kernel(const ColsArgs a) {
 #pragma unroll
       for (int j = 0; j < RT; ++j) {
         const int col = j * 8 + 2 * t;
-        atomicAdd(a.out + static_cast<size_t>(orow) * RP + col, acc[kt][j][0] + acc[kt][j + RT][0]);
-        atomicAdd(a.out + static_cast<size_t>(orow) * RP + col + 1, acc[kt][j][1] + acc[kt][j + RT][1]);
-        atomicAdd(a.out + static_cast<size_t>(orow + 8) * RP + col, acc[kt][j][2] + acc[kt][j + RT][2]);
-        atomicAdd(a.out + static_cast<size_t>(orow + 8) * RP + col + 1, acc[kt][j][3] + acc[kt][j + RT][3]);
+        // 64-bit vector reductions (sm_90+): half as many atomics in the tail every CTA reaches at the same time
+        atomicAdd(reinterpret_cast<float2*>(a.out + static_cast<size_t>(orow) * RP + col),
+                  make_float2(acc[kt][j][0] + acc[kt][j + RT][0], acc[kt][j][1] + acc[kt][j + RT][1]));
+        atomicAdd(reinterpret_cast<float2*>(a.out + static_cast<size_t>(orow + 8) * RP + col),
+                  make_float2(acc[kt][j][2] + acc[kt][j + RT][2], acc[kt][j][3] + acc[kt][j + RT][3]));
       }
       if (a.colsum != nullptr && t == 0) {
         atomicAdd(a.colsum + kc, acc[kt][NT][0]);
