@@ -22,16 +22,14 @@ __device__ __forceinline__ int clip8(int v) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// src [B, H, W, 3] -> dst [B, H, OW, 3]; one thread per (image, row, output column)
+// src [B, H, W, 3] -> dst [B, H, OW, 3]; one block per (image, input row), threads over the output columns
 __global__ void __launch_bounds__(256)
 resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int* __restrict__ bounds,
-                const int* __restrict__ kk, int ksize, long total, int H, int W, int OW) {
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int xx = static_cast<int>(i % OW);
-    const long row = i / OW;                  // b * H + y
-    const int xmin = bounds[2 * xx], xmax = bounds[2 * xx + 1];
-    const int* k = kk + static_cast<long>(xx) * ksize;
+                const int* __restrict__ kk, int ksize, int W, int OW) {
+  const long row = blockIdx.x;                // b * H + y
+  for (int xx = threadIdx.x; xx < OW; xx += blockDim.x) {
+    const int xmin = __ldg(bounds + 2 * xx), xmax = __ldg(bounds + 2 * xx + 1);
+    const int* k = kk + xx * ksize;
     const uint8_t* p = src + (row * W + xmin) * 3;
     int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
     for (int x = 0; x < xmax; ++x) {
@@ -40,28 +38,29 @@ resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, cons
       s1 += p[3 * x + 1] * w;
       s2 += p[3 * x + 2] * w;
     }
-    uint8_t* o = dst + i * 3;
+    uint8_t* o = dst + (row * OW + xx) * 3;
     o[0] = static_cast<uint8_t>(clip8(s0));
     o[1] = static_cast<uint8_t>(clip8(s1));
     o[2] = static_cast<uint8_t>(clip8(s2));
   }
 }
 
-// src [B, H, OW, 3] uint8 -> out [B, 3, OH, OW] fp32 normalised (vertical pass when bounds != nullptr)
+// src [B, H, OW, 3] uint8 -> out [B, 3, OH, OW] fp32 normalised (vertical pass when bounds != nullptr);
+// one block per (image, output row): the taps of the row are uniform across the block
 __global__ void __launch_bounds__(256)
 resize_v_norm_kernel(const uint8_t* __restrict__ src, float* __restrict__ out, uint8_t* __restrict__ out_u8,
-                     const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, long total, int H, int OH,
-                     int OW, float m0, float m1, float m2, float d0, float d1, float d2) {
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int xx = static_cast<int>(i % OW);
-    const int yy = static_cast<int>((i / OW) % OH);
-    const long b = i / (static_cast<long>(OW) * OH);
+                     const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int H, int OH, int OW,
+                     float m0, float m1, float m2, float d0, float d1, float d2) {
+  const int yy = blockIdx.x % OH;
+  const long b = blockIdx.x / OH;
+  const int ymin = bounds != nullptr ? __ldg(bounds + 2 * yy) : yy;
+  const int ymax = bounds != nullptr ? __ldg(bounds + 2 * yy + 1) : 1;
+  const int* k = kk + yy * ksize;
+  const long plane = static_cast<long>(OH) * OW;
+  for (int xx = threadIdx.x; xx < OW; xx += blockDim.x) {
+    const uint8_t* p = src + ((b * H + ymin) * OW + xx) * 3;
     int v0, v1, v2;
     if (bounds != nullptr) {
-      const int ymin = bounds[2 * yy], ymax = bounds[2 * yy + 1];
-      const int* k = kk + static_cast<long>(yy) * ksize;
-      const uint8_t* p = src + ((b * H + ymin) * OW + xx) * 3;
       int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
       for (int y = 0; y < ymax; ++y) {
         const int w = __ldg(k + y);
@@ -72,15 +71,14 @@ resize_v_norm_kernel(const uint8_t* __restrict__ src, float* __restrict__ out, u
       }
       v0 = clip8(s0); v1 = clip8(s1); v2 = clip8(s2);
     } else {
-      const uint8_t* p = src + ((b * H + yy) * OW + xx) * 3;
       v0 = p[0]; v1 = p[1]; v2 = p[2];
     }
+    const long pix = static_cast<long>(blockIdx.x) * OW + xx;
     if (out_u8 != nullptr) {                  // the resized uint8 image (parity checks against Pillow)
-      uint8_t* o = out_u8 + i * 3;
+      uint8_t* o = out_u8 + pix * 3;
       o[0] = static_cast<uint8_t>(v0); o[1] = static_cast<uint8_t>(v1); o[2] = static_cast<uint8_t>(v2);
     }
     if (out != nullptr) {
-      const long plane = static_cast<long>(OH) * OW;
       float* o = out + b * 3 * plane + static_cast<long>(yy) * OW + xx;
       o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v0), 255.0f), m0), d0);
       o[plane] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v1), 255.0f), m1), d1);
@@ -97,19 +95,14 @@ int resize_norm_launch(const uint8_t* src, int B, int H, int W, const int* xboun
   if (B <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) return -80;
   if ((xbounds == nullptr) != (W == OW) || (ybounds == nullptr) != (H == OH)) return -80;   // a pass is skipped only at equal size
   if (xbounds != nullptr && tmp == nullptr) return -80;
+  if (static_cast<long>(B) * H > 2147483647L || static_cast<long>(B) * OH > 2147483647L) return -80;
   const uint8_t* cur = src;
   if (xbounds != nullptr) {
-    const long total = static_cast<long>(B) * H * OW;
-    long grid = (total + 255) / 256;
-    if (grid > 148L * 32) grid = 148L * 32;
-    resize_h_kernel<<<static_cast<int>(grid), 256, 0, st>>>(src, tmp, xbounds, xk, xksize, total, H, W, OW);
+    resize_h_kernel<<<B * H, 256, 0, st>>>(src, tmp, xbounds, xk, xksize, W, OW);
     cur = tmp;
   }
-  const long total = static_cast<long>(B) * OH * OW;
-  long grid = (total + 255) / 256;
-  if (grid > 148L * 32) grid = 148L * 32;
-  resize_v_norm_kernel<<<static_cast<int>(grid), 256, 0, st>>>(cur, out, out_u8, ybounds, yk, yksize, total, H, OH, OW, mean[0],
-                                                               mean[1], mean[2], stdv[0], stdv[1], stdv[2]);
+  resize_v_norm_kernel<<<B * OH, 256, 0, st>>>(cur, out, out_u8, ybounds, yk, yksize, H, OH, OW, mean[0], mean[1], mean[2],
+                                               stdv[0], stdv[1], stdv[2]);
   return cudaGetLastError() == cudaSuccess ? 0 : -81;
 }
 
