@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Diagnostics: where does the bf16 path's error against the fp32 oracle come from?"""
+"""Diagnostics (test infrastructure, not collected by pytest): where does the bf16 path's error against the fp32
+oracle come from?  python tests/parity_diag.py"""
 import os
 import sys
 import warnings

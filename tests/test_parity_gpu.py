@@ -86,7 +86,7 @@ def test_reduced_depth_geometries_vs_oracle(geom, batch, scale):
     logits, loss, grads = run_step(vit, x, y)
     o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, scale)
     # The 1e-2 bar is defined on the full-depth models (tested above at 4.9e-3).  Two/three-block models have far
-    # fewer terms for the bf16 roundings to average over and sit at 4e-3..1e-2 (tools/parity_diag.py; the same
+    # fewer terms for the bf16 roundings to average over and sit at 4e-3..1e-2 (tests/parity_diag.py; the same
     # numbers come out of a CPU emulation that rounds an fp32 forward at the kernels' rounding points), so they
     # get 1.5e-2 -- the gradient-cosine bar stays at 0.999 for every tensor.
     check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, str(geom), logits_tol=1.5e-2)
