@@ -46,13 +46,19 @@ def train(args, model, dl, tdl, opt, epochs, world_size=1, rank=0):
     """Reference vit_cp.py:19-70."""
     model.train()
     acc, old_name, use_sched = 0.0, None, True
+    # The loader drops the last partial batch (vtab.py:84-88), so every step has the same shape: zero_grad + forward +
+    # CE + backward are captured once into a CUDA graph and replayed (at the reference's batch of 64 the ~470 launches
+    # of a step take longer to enqueue from Python than to run).
+    step = None
     for epoch in range(epochs):
         for x, y in dl:
             x, y = to_device(x, y)
             if world_size > 1:
                 lo, hi = T.shard_batch(x.shape[0], rank, world_size)
                 x, y = x[lo:hi], y[lo:hi]
-            loss = T.train_step(model, opt, x, y, world_size)
+            if step is None and not args.no_graph:
+                step = T.GraphedStep(model, opt, x, y, world_size)
+            loss = step(x, y) if step is not None else T.train_step(model, opt, x, y, world_size)
             if use_sched:
                 opt.param_groups[0]["lr"] = T.cosine_lr(epoch, base_lr=args.lr)
         if rank == 0:
@@ -82,6 +88,7 @@ def _parse_args():
     p.add_argument("--batch-size", type=int, default=64, help="global train batch")
     p.add_argument("--synthetic", action="store_true", help="force VTAB-shaped synthetic data")
     p.add_argument("--no-merge", action="store_true", help="evaluate without folding the CP delta into W")
+    p.add_argument("--no-graph", action="store_true", help="enqueue every train step eagerly (no CUDA graph replay)")
     p.add_argument("--gpu-preprocess", action="store_true",
                    help="decode on the CPU, resize + normalise on the GPU (bit-identical to the reference's transforms)")
     return p.parse_args()
