@@ -145,7 +145,8 @@ def main(sd=None):
         if old_name is not None:
             os.remove(old_name)
         th.save(vit.state_dict(), f"./vit_{name}_{round(args.best_acc, 5)}_seed_{seed}.pt")
-    print(f"Accuracy: {args.best_acc}")
+    if rank == 0:
+        print(f"Accuracy: {args.best_acc}")
 
 
 if __name__ == "__main__":
