@@ -53,7 +53,7 @@ _SIGS = {
     "cara_adamw_step": (C.c_int, [_P, _P, _P, _P, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_float, _P]),
     "cara_sgemm": (C.c_int, [_P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P, C.c_int, C.c_int,
-                             C.c_int, C.c_float, C.c_float, _P]),
+                             C.c_int, C.c_float, C.c_float, _P, C.c_long, _P]),
 }
 
 _lib = None

@@ -136,8 +136,10 @@ int cara_adamw_step(float* p, const float* g, float* m, float* v, long n, float 
   CARA_RET(cara::adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale, CARA_STREAM(stream)), "cara_adamw_step");
 }
 int cara_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
-               const float* bias, int M, int N, int K, float alpha, float beta, void* stream) {
-  CARA_RET(cara::sgemm_launch(A, ars, acs, B, brs, bcs, C, ldc, bias, M, N, K, alpha, beta, CARA_STREAM(stream)), "cara_sgemm");
+               const float* bias, int M, int N, int K, float alpha, float beta, float* workspace, long workspace_floats,
+               void* stream) {
+  CARA_RET(cara::sgemm_launch(A, ars, acs, B, brs, bcs, C, ldc, bias, M, N, K, alpha, beta, workspace, workspace_floats,
+                              CARA_STREAM(stream)), "cara_sgemm");
 }
 
 }  // extern "C"

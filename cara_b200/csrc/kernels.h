@@ -124,7 +124,8 @@ int merge_launch(const float* W, const float* A, const float* Bf, const float* c
 int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
                  float wd, int step, float gscale, cudaStream_t st);
 int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
-                 const float* bias, int M, int N, int K, float alpha, float beta, cudaStream_t st);
+                 const float* bias, int M, int N, int K, float alpha, float beta, float* ws, long ws_floats,
+                 cudaStream_t st);
 
 // GPU input pipeline (preprocess.cu): Pillow-exact bicubic Resize + ToTensor + Normalize on uint8 HWC images
 int resize_norm_launch(const uint8_t* src, int B, int H, int W, const int* xbounds, const int* xk, int xksize,

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -179,11 +180,11 @@ int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr,
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, long ars, long acs, const float* __restrict__ B, long brs, long bcs,
              float* __restrict__ C, long ldc, const float* __restrict__ bias, int M, int N, int K, float alpha,
-             float beta, int kper) {
+             float beta, int kper, float* __restrict__ ws) {
   __shared__ float As[16][65], Bs[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  // split-K (gridDim.z > 1): this CTA reduces k in [kbeg, kend) and adds its partial sum atomically into a zeroed C
+  // split-K (gridDim.z > 1): this CTA reduces k in [kbeg, kend) into its own slice of the workspace
   const int kbeg = blockIdx.z * kper;
   const int kend = (kbeg + kper < K) ? kbeg + kper : K;
   K = kend;
@@ -214,9 +215,8 @@ sgemm_kernel(const float* __restrict__ A, long ars, long acs, const float* __res
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = alpha * acc[i][j];
-      if (gridDim.z > 1) {
-        if (bias != nullptr && blockIdx.z == 0) v += bias[n];
-        atomicAdd(C + m * ldc + n, v);
+      if (gridDim.z > 1) {                      // split-K: partial sums, reduced in a fixed order by sgemm_reduce_kernel
+        ws[(static_cast<long>(blockIdx.z) * M + m) * N + n] = v;
         continue;
       }
       if (bias != nullptr) v += bias[n];
@@ -225,22 +225,42 @@ sgemm_kernel(const float* __restrict__ A, long ars, long acs, const float* __res
     }
   }
 }
+// C[m,n] = sum_z ws[z,m,n] + bias[n]: the split-K partial sums in a fixed order (no atomics: every run of the same step
+// produces the same bits -- fp32 noise in the logits would flip bf16 roundings all the way down the backward pass)
+__global__ void __launch_bounds__(256)
+sgemm_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, const float* __restrict__ bias, long MN, int N,
+                    int splits) {
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < MN; i += gridDim.x * 256L) {
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += ws[z * MN + i];
+    if (bias != nullptr) v += bias[i % N];
+    C[i] = v;
+  }
+}
+
 int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
-                 const float* bias, int M, int N, int K, float alpha, float beta, cudaStream_t st) {
+                 const float* bias, int M, int N, int K, float alpha, float beta, float* ws, long ws_floats,
+                 cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return -69;
   const int gx = (N + 63) / 64, gy = (M + 63) / 64;
   // The classifier head's three GEMMs (e.g. 256 x 100 x 768) fill 8-48 CTAs and are pure latency chains over K:
-  // split K across ~2 CTAs per SM when C is a plain contiguous output.
+  // split K across ~2 CTAs per SM when C is a plain contiguous output and the caller lent a workspace.
   int splits = 1;
-  if (beta == 0.f && ldc == N && gx * gy < 74 && K >= 128) {
+  if (ws != nullptr && beta == 0.f && ldc == N && gx * gy < 74 && K >= 128) {
     splits = (2 * 148) / (gx * gy);
     if (splits > K / 32) splits = K / 32;
+    while (splits > 1 && static_cast<long>(splits) * M * N > ws_floats) --splits;
     if (splits < 1) splits = 1;
   }
   int kper = ((K + splits - 1) / splits + 15) / 16 * 16;
   splits = (K + kper - 1) / kper;
-  if (splits > 1 && cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, st) != cudaSuccess) return -70;
-  sgemm_kernel<<<dim3(gx, gy, splits), 256, 0, st>>>(A, ars, acs, B, brs, bcs, C, ldc, bias, M, N, K, alpha, beta, kper);
+  sgemm_kernel<<<dim3(gx, gy, splits), 256, 0, st>>>(A, ars, acs, B, brs, bcs, C, ldc, bias, M, N, K, alpha, beta, kper, ws);
+  if (splits > 1) {
+    const long MN = static_cast<long>(M) * N;
+    long grid = (MN + 255) / 256;
+    if (grid > 148 * 4) grid = 148 * 4;
+    sgemm_reduce_kernel<<<static_cast<int>(grid), 256, 0, st>>>(ws, C, bias, MN, N, splits);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -70;
 }
 

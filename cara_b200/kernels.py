@@ -257,6 +257,17 @@ def adamw_step(p, g, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=
                                     betas[1], eps, weight_decay, step, gscale, st), "cara_adamw_step")
 
 
+_SGEMM_WS_FLOATS = 1 << 22          # 16 MB of split-K partial sums per device (stream-ordered reuse)
+_sgemm_ws = {}
+
+
+def _sgemm_workspace(device):
+    ws = _sgemm_ws.get(device)
+    if ws is None:
+        ws = _sgemm_ws[device] = torch.empty(_SGEMM_WS_FLOATS, device=device, dtype=F32)
+    return ws
+
+
 def sgemm(A, B, bias=None, out=None, alpha=1.0, beta=0.0):
     """fp32 C = alpha * A @ B + beta * C + bias for arbitrary-stride 2-D views."""
     st = _prep(A)
@@ -265,6 +276,8 @@ def sgemm(A, B, bias=None, out=None, alpha=1.0, beta=0.0):
     assert A.dtype == F32 and B.dtype == F32 and B.shape[0] == K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=F32)
+    ws = _sgemm_workspace(A.device) if M * N <= _SGEMM_WS_FLOATS // 4 else None   # small outputs only (split-K)
     L.check(L.lib().cara_sgemm(A.data_ptr(), A.stride(0), A.stride(1), B.data_ptr(), B.stride(0), B.stride(1),
-                               out.data_ptr(), out.stride(0), _p(bias), M, N, K, alpha, beta, st), "cara_sgemm")
+                               out.data_ptr(), out.stride(0), _p(bias), M, N, K, alpha, beta, _p(ws),
+                               0 if ws is None else ws.numel(), st), "cara_sgemm")
     return out

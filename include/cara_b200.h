@@ -144,9 +144,12 @@ CARA_API int cara_adamw_step(float* p, const float* g, float* m, float* v, long 
                              float beta2, float eps, float weight_decay, int step, float gscale, void* stream);
 
 /* Plain fp32 GEMM with general strides for the tiny trainable head (vit_cp.py:166):
- *   C[m,n] = alpha * sum_k A[m*ars + k*acs] * B[k*brs + n*bcs] + beta * C[m,n] + bias[n]. */
+ *   C[m,n] = alpha * sum_k A[m*ars + k*acs] * B[k*brs + n*bcs] + beta * C[m,n] + bias[n].
+ * workspace (optional, device, workspace_floats fp32 elements, borrowed for the call): lets small problems split K
+ * over more CTAs; the partial sums are reduced in a fixed order, so results are reproducible bit for bit. */
 CARA_API int cara_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
-                        const float* bias, int M, int N, int K, float alpha, float beta, void* stream);
+                        const float* bias, int M, int N, int K, float alpha, float beta, float* workspace,
+                        long workspace_floats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Diagnostics (test infrastructure, not collected by pytest): where does the bf16 path's error against the fp32
-oracle come from?  python tests/parity_diag.py"""
+oracle come from?  python tests/diag/parity_diag.py"""
 import os
 import sys
 import warnings
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cara_oracle as O  # noqa: E402
 from tests.test_parity_gpu import build, run_step, rel, cos  # noqa: E402
 

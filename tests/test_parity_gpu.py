@@ -86,7 +86,7 @@ def test_reduced_depth_geometries_vs_oracle(geom, batch, scale):
     logits, loss, grads = run_step(vit, x, y)
     o_logits, o_loss, o_grads = O.loss_and_grads(st, g, x, y, scale)
     # The 1e-2 bar is defined on the full-depth models (tested above at 4.9e-3).  Two/three-block models have far
-    # fewer terms for the bf16 roundings to average over and sit at 4e-3..1e-2 (tests/parity_diag.py; the same
+    # fewer terms for the bf16 roundings to average over and sit at 4e-3..1e-2 (tests/diag/parity_diag.py; the same
     # numbers come out of a CPU emulation that rounds an fp32 forward at the kernels' rounding points), so they
     # get 1.5e-2 -- the gradient-cosine bar stays at 0.999 for every tensor.
     check_against(logits, loss, grads, o_logits, float(o_loss), o_grads, str(geom), logits_tol=1.5e-2)
@@ -270,3 +270,36 @@ def test_exact_weight_dropout_mode_replays_through_oracle(monkeypatch):
     # and the masks matter: the same step without them is measurably different
     n_logits, _, _ = O.loss_and_grads(st, g, x, y, 1.0)
     assert rel(n_logits, o_logits) > 3 * rel(logits, o_logits)
+
+
+def test_graphed_step_matches_eager_steps():
+    """bench.py and vit_cp.py replay zero_grad + forward + CE + backward from one CUDA graph
+    (cara_b200.train.GraphedStep): three optimizer steps through the graph must land on the same parameters and
+    losses as three eagerly enqueued steps (atomics reorder fp32 sums, hence a tolerance rather than equality)."""
+    from cara_b200 import train as T
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    batches = [O.synthetic_batch(g, 4, seed=100 + i) for i in range(3)]
+    results = []
+    for graphed in (False, True):
+        vit, _ = build(g, 1.0)
+        vit.train()                                   # drop_path 0: the two runs are deterministic up to atomics
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            opt = T.FusedAdamW(T.FlatTrainable(T.freeze_backbone(vit)), lr=1e-3, weight_decay=1e-4)
+            x0, y0 = batches[0][0].cuda(), batches[0][1].cuda()
+            step = T.GraphedStep(vit, opt, x0, y0) if graphed else (lambda x, y: T.train_step(vit, opt, x, y))
+            losses, grad1 = [], None
+            for x, y in batches:
+                losses.append(float(step(x.cuda(), y.cuda())))
+                if grad1 is None:
+                    grad1 = opt.flat.grad.detach().cpu().clone()     # gradient of the first step (zeroed at the next one)
+        if graphed:
+            assert step.launches_per_replay > 50
+        results.append((losses, grad1, opt.flat.flat.detach().cpu().clone()))
+    (l_e, g_e, p_e), (l_g, g_g, p_g) = results
+    assert max(abs(a - b) for a, b in zip(l_e, l_g)) < 2e-3, (l_e, l_g)
+    assert l_e[0] != l_e[2]                           # the parameters really moved between the steps
+    assert rel(g_g, g_e) < 1e-5, rel(g_g, g_e)        # same kernels, same inputs: only the atomics' order differs
+    # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is rounding noise may flip
+    assert rel(p_g, p_e) < 1e-3, rel(p_g, p_e)
