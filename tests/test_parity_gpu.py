@@ -303,3 +303,22 @@ def test_graphed_step_matches_eager_steps():
     assert rel(g_g, g_e) < 1e-5, rel(g_g, g_e)        # same kernels, same inputs: only the atomics' order differs
     # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is rounding noise may flip
     assert rel(p_g, p_e) < 1e-3, rel(p_g, p_e)
+
+
+def test_identical_steps_are_reproducible():
+    """Two fresh models, same weights, same batch: forward and the dX chain have no atomics, so the logits are bit
+    identical and the gradients differ only by the order of the fp32 atomics of the factor-gradient reductions."""
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    x, y = O.synthetic_batch(g, 4, seed=100)
+    outs = []
+    for _ in range(3):
+        vit, _ = build(g, 1.0)
+        vit.train()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            outs.append(run_step(vit, x, y))
+    for logits, loss, grads in outs[1:]:
+        assert torch.equal(logits, outs[0][0]) and loss == outs[0][1]
+        for k in grads:
+            assert rel(grads[k], outs[0][2][k]) < 2e-6, (k, rel(grads[k], outs[0][2][k]))
