@@ -49,6 +49,7 @@ _SIGS = {
                                         C.c_int, C.c_int, _P, _P, _P]),
     "cara_patchify": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cara_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_factor_operands": (C.c_int, [_P, _P, _P, C.c_long, C.c_int, C.c_int, C.c_int, _P]),
     "cara_merge_weights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cara_adamw_step": (C.c_int, [_P, _P, _P, _P, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_float, _P]),

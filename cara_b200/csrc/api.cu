@@ -127,6 +127,10 @@ int cara_assemble_tokens(const void* pe, const float* cls, const float* pos, flo
                          void* stream) {
   CARA_RET(cara::assemble_launch(static_cast<const bf16*>(pe), cls, pos, x, B, N, C, CARA_STREAM(stream)), "cara_assemble_tokens");
 }
+int cara_factor_operands(const float* F, void* ext, void* t2, long batch, int rows, int R, int Rp, void* stream) {
+  CARA_RET(cara::factor_operands_launch(F, static_cast<bf16*>(ext), static_cast<bf16*>(t2), batch, rows, R, Rp,
+                                        CARA_STREAM(stream)), "cara_factor_operands");
+}
 int cara_merge_weights(const float* W, const float* A, const float* Bf, const float* cs, void* Weff, int N, int K,
                        int slices, int R, void* stream) {
   CARA_RET(cara::merge_launch(W, A, Bf, cs, static_cast<bf16*>(Weff), N, K, slices, R, CARA_STREAM(stream)), "cara_merge_weights");

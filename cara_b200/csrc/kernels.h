@@ -127,6 +127,9 @@ int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, l
                  const float* bias, int M, int N, int K, float alpha, float beta, float* ws, long ws_floats,
                  cudaStream_t st);
 
+int factor_operands_launch(const float* F, __nv_bfloat16* ext, __nv_bfloat16* t2, long batch, int rows, int R, int Rp,
+                           cudaStream_t st);
+
 // GPU input pipeline (preprocess.cu): Pillow-exact bicubic Resize + ToTensor + Normalize on uint8 HWC images
 int resize_norm_launch(const uint8_t* src, int B, int H, int W, const int* xbounds, const int* xk, int xksize,
                        const int* ybounds, const int* yk, int yksize, uint8_t* tmp, float* out, uint8_t* out_u8,

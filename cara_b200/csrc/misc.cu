@@ -107,6 +107,38 @@ int assemble_launch(const __nv_bfloat16* pe, const float* cls, const float* pos,
   return launch_pdl_f<16>(assemble_kernel, dim3(148 * 8), dim3(256), 0, st, pe, cls, pos, x, B, N, C) == cudaSuccess ? 0 : -63;
 }
 
+// ---------------------------------------------------------------- staged factor operands
+// F fp32 [batch, rows, R] -> ext bf16 [batch, rows, 3Rp] = [hi | hi | lo] (adapter segment of the GEMM) and
+// t2 bf16 [batch, 2Rp, rows] = [hi^T ; lo^T] (skinny kernels), hi + lo ~ F to ~16 mantissa bits, zero padded to Rp.
+// One launch per factor instead of the ~10 elementwise / cat / transpose kernels of the torch formulation.
+__global__ void __launch_bounds__(256)
+factor_operands_kernel(const float* __restrict__ F, __nv_bfloat16* __restrict__ ext, __nv_bfloat16* __restrict__ t2,
+                       long total, int rows, int R, int Rp) {
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
+    const int r = static_cast<int>(i % Rp);
+    const long br = i / Rp;                       // batch * rows + row
+    const int row = static_cast<int>(br % rows);
+    const long b = br / rows;
+    const float v = r < R ? F[br * R + r] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* e = ext + br * 3 * Rp;
+    e[r] = hi; e[Rp + r] = hi; e[2 * Rp + r] = lo;
+    __nv_bfloat16* t = t2 + b * 2 * Rp * rows;
+    t[static_cast<long>(r) * rows + row] = hi;
+    t[static_cast<long>(Rp + r) * rows + row] = lo;
+  }
+}
+int factor_operands_launch(const float* F, __nv_bfloat16* ext, __nv_bfloat16* t2, long batch, int rows, int R, int Rp,
+                           cudaStream_t st) {
+  if (batch <= 0 || rows <= 0 || R <= 0 || Rp < R) return -64;
+  const long total = batch * rows * Rp;
+  long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  factor_operands_kernel<<<static_cast<int>(grid), 256, 0, st>>>(F, ext, t2, total, rows, R, Rp);
+  return cudaGetLastError() == cudaSuccess ? 0 : -65;
+}
+
 // ---------------------------------------------------------------- eval-mode merge
 // Weff[n, k] = W[n, k] + sum_r (Bf[n mod w, r] * cs[n / w, r]) * A[k, r]      W fp32 -> Weff bf16
 template <int R>

@@ -120,10 +120,23 @@ def split_bf16(F):
 
 def factor_operands(F, Rp):
     """fp32 factor [..., rows, R] -> (ext bf16 [..., rows, 3Rp] = [hi|hi|lo], t2 bf16 [..., 2Rp, rows] = [hi^T; lo^T])."""
-    Fp = torch.nn.functional.pad(F.detach().float(), (0, Rp - F.shape[-1]))
-    hi, lo = split_bf16(Fp)
-    ext = torch.cat([hi, hi, lo], dim=-1).contiguous()
-    t2 = torch.cat([hi.transpose(-1, -2), lo.transpose(-1, -2)], dim=-2).contiguous()
+    F = F.detach().float().contiguous()
+    if not F.is_cuda:                     # host-side staging tests: the same arithmetic in torch
+        Fp = torch.nn.functional.pad(F, (0, Rp - F.shape[-1]))
+        hi, lo = split_bf16(Fp)
+        ext = torch.cat([hi, hi, lo], dim=-1).contiguous()
+        t2 = torch.cat([hi.transpose(-1, -2), lo.transpose(-1, -2)], dim=-2).contiguous()
+        return ext, t2
+    st = _prep(F)
+    rows, R = F.shape[-2], F.shape[-1]
+    lead = tuple(F.shape[:-2])
+    batch = 1
+    for d in lead:
+        batch *= d
+    ext = torch.empty(lead + (rows, 3 * Rp), device=F.device, dtype=BF16)
+    t2 = torch.empty(lead + (2 * Rp, rows), device=F.device, dtype=BF16)
+    L.check(L.lib().cara_factor_operands(F.data_ptr(), ext.data_ptr(), t2.data_ptr(), batch, rows, R, Rp, st),
+            "cara_factor_operands")
     return ext, t2
 
 

@@ -86,9 +86,17 @@ def staged(model):
     cs_fc1 = s_m * (f["CP_R2"] * f["CP_P1"][mi[:, None] + r4])                            # [Lm,4,R]
     a_fc2 = (f["CP_P1"][mi[:, None] + 4 + r4][:, :, None, :] * f["CP_P2"][None, None]).reshape(Lm, 4 * C, R)
     cs_fc2 = s_m * f["CP_R2"].view(1, 1, R).expand(Lm, 1, R)
-    b_proj = torch.stack([m.proj.bias.detach().float() for m in attn]) + s_a.view(La, 1) * f["CP_bias1"]
-    b_fc1 = torch.stack([m.fc1.bias.detach().float() for m in mlp]) + s_m.view(Lm, 1) * f["CP_bias2"]
-    b_fc2 = torch.stack([m.fc2.bias.detach().float() for m in mlp]) + s_m.view(Lm, 1) * f["CP_bias3"]
+    # the frozen biases never change during fine-tuning: stack them once per (pointer, version) set
+    bkey = key[4]
+    bcache = model.__dict__.get("_cara_stage_bias")
+    if bcache is None or bcache[0] != bkey:
+        bcache = (bkey, torch.stack([m.proj.bias.detach().float() for m in attn]),
+                  torch.stack([m.fc1.bias.detach().float() for m in mlp]),
+                  torch.stack([m.fc2.bias.detach().float() for m in mlp]))
+        model.__dict__["_cara_stage_bias"] = bcache
+    b_proj = bcache[1] + s_a.view(La, 1) * f["CP_bias1"]
+    b_fc1 = bcache[2] + s_m.view(Lm, 1) * f["CP_bias2"]
+    b_fc2 = bcache[3] + s_m.view(Lm, 1) * f["CP_bias3"]
 
     with torch.no_grad():
         a2_pad, a2_t = K.factor_operands(f["CP_A2"], Rp)

@@ -134,6 +134,13 @@ CARA_API int cara_patchify(const float* img, void* patches, int B, int Cin, int 
 CARA_API int cara_assemble_tokens(const void* pe, const float* cls, const float* pos, float* x, int B, int N, int C,
                                   void* stream);
 
+/* Staging of one CP factor for the kernels above: F fp32 [batch, rows, R] ->
+ *   ext bf16 [batch, rows, 3Rp] = [hi | hi | lo]   (B1 operand of cara_gemm_cp's adapter segment)
+ *   t2  bf16 [batch, 2Rp, rows] = [hi^T ; lo^T]    (At2 / Bt2 operand of cara_adapter_rows_*)
+ * with hi = bf16(F), lo = bf16(F - hi), zero padded from R to Rp columns. */
+CARA_API int cara_factor_operands(const float* F, void* ext, void* t2, long batch, int rows, int R, int Rp,
+                                  void* stream);
+
 /* Eval-mode merge (the reference re-materialises the delta every forward, cara.py:27,52,76,88):
  *   Weff[n,k] = W[n,k] + sum_r Bf[n mod w, r] cs[n / w, r] A[k, r],  W fp32 [N,K] -> Weff bf16 [N,K]. */
 CARA_API int cara_merge_weights(const float* W, const float* A, const float* Bf, const float* cs, void* Weff, int N,

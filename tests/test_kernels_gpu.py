@@ -287,3 +287,15 @@ def test_fp32_mode_attention_and_gelu(K, B, N, H, D):
     dy = torch.randn_like(u)
     yd.backward(dy.double())
     assert rel(K.gelu_f32(u, dy=dy), ud.grad) < 2e-6
+
+
+@pytest.mark.parametrize("shape,Rp", [((768, 16), 16), ((768, 8), 16), ((12, 3072, 16), 16), ((2, 1024, 20), 32), ((5, 7), 16)])
+def test_factor_operands_kernel_matches_torch_formulation(K, shape, Rp):
+    """cara_factor_operands (pad + bf16 hi/lo split + both operand layouts in one launch) is bit-identical to the
+    torch formulation the host-side staging tests use."""
+    g = torch.Generator().manual_seed(5)
+    F = torch.randn(*shape, generator=g) * 0.3
+    ext_c, t2_c = K.factor_operands(F, Rp)                 # CPU tensors -> torch formulation
+    ext_g, t2_g = K.factor_operands(F.cuda(), Rp)          # CUDA tensors -> the kernel
+    assert ext_g.shape == ext_c.shape and t2_g.shape == t2_c.shape
+    assert torch.equal(ext_g.cpu(), ext_c) and torch.equal(t2_g.cpu(), t2_c)
