@@ -176,10 +176,12 @@ def run_cuda(args):
     # ------------------------------------------------------------ device-resident throughput ("value")
     # zero_grad + forward + CE + backward are replayed from one CUDA graph (cara_b200.train.GraphedStep); the
     # all-reduce and the fused AdamW kernel are launched eagerly after each replay.
+    if args.accum < 1 or B % args.accum != 0 or (args.no_graph and args.accum != 1):
+        raise SystemExit("--accum must divide the per-GPU batch (and needs the CUDA-graph step)")
     if args.no_graph:
         step = lambda x, y: T.train_step(vit, opt, x, y, world)          # noqa: E731
     else:
-        step = T.GraphedStep(vit, opt, dev_x[0], dev_y[0], world)
+        step = T.GraphedStep(vit, opt, dev_x[0][:B // args.accum], dev_y[0][:B // args.accum], world, accumulate=args.accum)
     for i in range(args.warmup):
         step(dev_x[i % 2], dev_y[i % 2])
     barrier()
@@ -202,8 +204,9 @@ def run_cuda(args):
     # ------------------------------------------------------------ roofline of the dominant kernel: the same step run
     # eagerly with CUDA events around every fused-projection launch (events inside a replayed graph cannot be timed)
     K.gemm_events = []
+    mb = B // args.accum                                      # (one micro-batch when gradients are accumulated)
     for i in range(2):
-        T.train_step(vit, opt, dev_x[i % 2], dev_y[i % 2], world)
+        T.train_step(vit, opt, dev_x[i % 2][:mb], dev_y[i % 2][:mb], world)
     torch.cuda.synchronize()
     gemm_events, K.gemm_events = K.gemm_events, None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
@@ -273,7 +276,7 @@ def run_cuda(args):
                    "drop_path": 0.1,
                    "weight_dropout": "not applied (documented deviation; --weight-dropout exact selects the slow path)"
                    if args.weight_dropout == "skip" else "exact (reference semantics: 3 GEMMs per projection)",
-                   "cuda_graph": not args.no_graph,
+                   "cuda_graph": not args.no_graph, "micro_batches": args.accum,
                    "algorithmic_gflop_per_image": cfg["gflop_per_image"]},
         "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 8), "d2h_bytes_per_step": 4,
@@ -424,6 +427,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weight-dropout", default="skip", choices=["skip", "exact"],
                     help="exact: the reference's nn.Dropout(0.1) on the materialised delta weights (slow path)")
+    ap.add_argument("--accum", type=int, default=1,
+                    help="micro-batches per optimizer step (the per-GPU batch is split; activations kept for one)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

@@ -126,8 +126,11 @@ class GraphedStep:
     Inputs are copied into the graph's static buffers on the launching stream before each replay.
     """
 
-    def __init__(self, model, opt, x, y, world_size=1, warmup=3):
-        self.model, self.opt, self.world_size = model, opt, world_size
+    def __init__(self, model, opt, x, y, world_size=1, warmup=3, accumulate=1):
+        """``accumulate`` = k > 1: every call takes k micro-batches of the captured shape (x: [k*B, ...]) and sums
+        their gradients before the single all-reduce + AdamW step (activations are kept for one micro-batch only:
+        ViT-L at 1,024 images per GPU does not fit otherwise).  The loss returned is the mean over the k replays."""
+        self.model, self.opt, self.world_size, self.accumulate = model, opt, world_size, int(accumulate)
         self.x = torch.empty_like(x)
         self.y = torch.empty_like(y)
         self.x.copy_(x)
@@ -145,20 +148,34 @@ class GraphedStep:
         self.launches_per_replay = K.launch_count - before   # cara_* kernels inside the graph (bench: gpu_launches)
 
     def _fwd_bwd(self):
-        self.opt.zero_grad()
+        if self.accumulate == 1:
+            self.opt.zero_grad()              # inside the graph; with accumulation it happens once per call instead
         out = self.model(self.x)
         loss = torch.nn.functional.cross_entropy(out, self.y)
         loss.backward()
         return loss.detach()
 
     def __call__(self, x, y):
-        if x.shape != self.x.shape or y.shape != self.y.shape:
-            raise ValueError("GraphedStep was captured for batch shape %s" % (tuple(self.x.shape),))
-        if x.data_ptr() != self.x.data_ptr():
-            self.x.copy_(x, non_blocking=True)
-            self.y.copy_(y, non_blocking=True)
-        self.graph.replay()
-        K.launch_count += self.launches_per_replay
+        k, B = self.accumulate, self.x.shape[0]
+        if x.shape[0] != k * B or x.shape[1:] != self.x.shape[1:] or y.shape[0] != k * B:
+            raise ValueError("GraphedStep was captured for %d micro-batch(es) of shape %s" % (k, tuple(self.x.shape)))
+        if k == 1:
+            if x.data_ptr() != self.x.data_ptr():
+                self.x.copy_(x, non_blocking=True)
+                self.y.copy_(y, non_blocking=True)
+            self.graph.replay()
+            K.launch_count += self.launches_per_replay
+            loss = self.loss
+        else:
+            self.opt.zero_grad()
+            loss = None
+            for i in range(k):
+                self.x.copy_(x[i * B:(i + 1) * B], non_blocking=True)
+                self.y.copy_(y[i * B:(i + 1) * B], non_blocking=True)
+                self.graph.replay()
+                K.launch_count += self.launches_per_replay
+                loss = self.loss.clone() if loss is None else loss + self.loss
+            loss = loss / k
         allreduce_grads(self.opt.flat, self.world_size)
-        self.opt.step(grad_scale=1.0 / self.world_size)
-        return self.loss
+        self.opt.step(grad_scale=1.0 / (self.world_size * k))
+        return loss

@@ -322,3 +322,34 @@ def test_identical_steps_are_reproducible():
         assert torch.equal(logits, outs[0][0]) and loss == outs[0][1]
         for k in grads:
             assert rel(grads[k], outs[0][2][k]) < 2e-6, (k, rel(grads[k], outs[0][2][k]))
+
+
+def test_micro_batch_accumulation_equals_full_batch_step():
+    """GraphedStep(accumulate=2) on 2 x 3 images takes the same optimizer step as one eager step on all 6 (no
+    cross-sample operation exists on the path; only fp32 summation orders differ)."""
+    from cara_b200 import train as T
+    import warnings
+    g = O.Geometry(depth=2, rank=8, num_classes=10)
+    x, y = O.synthetic_batch(g, 6, seed=321)
+    x, y = x.cuda(), y.cuda()
+    res = []
+    for accumulate in (1, 2):
+        vit, _ = build(g, 1.0)
+        vit.train()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            opt = T.FusedAdamW(T.FlatTrainable(T.freeze_backbone(vit)), lr=1e-3, weight_decay=1e-4)
+            if accumulate == 1:
+                loss = T.train_step(vit, opt, x, y)
+                grad = opt.flat.grad.detach().cpu().clone()
+            else:
+                step = T.GraphedStep(vit, opt, x[:3], y[:3], accumulate=2)
+                loss = step(x, y)
+                grad = opt.flat.grad.detach().cpu().clone() / 2          # AdamW applies the 1/k through grad_scale
+        res.append((float(loss), grad, opt.flat.flat.detach().cpu().clone()))
+    (l1, g1, p1), (l2, g2, p2) = res
+    assert abs(l1 - l2) < 1e-4 * max(1.0, abs(l1)), (l1, l2)
+    assert rel(g2, g1) < 1e-5, rel(g2, g1)
+    assert rel(p2, p1) < 1e-5, rel(p2, p1)
+    with pytest.raises(ValueError):
+        step(x[:3], y[:3])
