@@ -9,7 +9,7 @@
 
 namespace cara {
 
-// Programmatic dependent launch (sm_90+), OFF by default (CARA_PDL=1 turns it on): every hot kernel can be launched
+// Programmatic dependent launch (sm_90+), OFF by default (CARA_PDL = bit mask of kernel families, see pdl_mask): every hot kernel can be launched
 // with "programmatic stream serialization"; it starts with pdl_wait() -- which returns once the preceding kernel in
 // the stream has completed and flushed -- and calls pdl_trigger() right after, so the NEXT kernel's CTAs are already
 // resident when this one ends.  Nothing touches global memory before pdl_wait().  Measured on the ViT-B/16 step
@@ -19,11 +19,6 @@ namespace cara {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
-inline bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("CARA_PDL"); on = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  return on == 1;
-}
 // pdl_mask bit per kernel family (CARA_PDL is a bit mask: 1 GEMM, 2 attention, 4 LayerNorm, 8 rows/cols, 16 small)
 inline int pdl_mask() {
   static int m = -1;
@@ -42,20 +37,6 @@ inline cudaError_t launch_pdl_f(void (*kernel)(KArgs...), dim3 grid, dim3 block,
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_mask() & FAMILY) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
-}
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 
