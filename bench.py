@@ -293,7 +293,7 @@ def run_cuda(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)
+            out["cpu_baseline"] = cpu_reference(args, steps=3, warmup=1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -373,43 +373,61 @@ def run_eval(args, cfg, vit, dev, world, rank):
         dist.destroy_process_group()
 
 
-def cpu_reference(args, steps, warmup):
-    """The reference's CPU path (oracle port of cara.py + timm/tensorly semantics, train mode as shipped:
-    weight dropout 0.1, DropPath 0.1, autograd through the materialised deltas, AdamW) on the host cores."""
+CPU_CONFIG = dict(embed_dim=768, depth=12, num_heads=12, patch=16, rank=8, batch=32)   # BASELINE.json configs[0]
+CPU_WORKLOAD = ("BASELINE configs[0]: ViT-B/16 CaRA rank=8 fp32 fwd+bwd+AdamW step on the host CPU, batch 32 synthetic "
+                "224x224, 100 classes, random-init weights, train mode as shipped (weight dropout 0.1, DropPath 0.1)")
+
+
+def cpu_reference(args, steps=3, warmup=1):
+    """The reference's CPU path at BASELINE config 1 exactly as BASELINE.md section 5 / SURVEY 8(d) specify it: the
+    loop body of vit_cp.py:45-50 (forward, CE, backward through the materialised deltas, AdamW(lr 1e-3, wd 1e-4) over
+    CP* + head) in train mode as shipped, ViT-B/16, rank 8, fp32, batch 32, all host threads, ``warmup`` untimed steps
+    then best of ``steps``.  The reference is pure Python on timm/tensorly, which are not in this image, so what runs
+    is the oracle port (oracle/cara_oracle.py, pinned to the reference's own outputs by tests/test_oracle_golden.py):
+    ``kind`` says "port".  Returns the steps / warm-ups actually executed."""
     import torch
     from oracle import cara_oracle as O
-    cfg = CONFIGS[args.config]
+    c = dict(CPU_CONFIG)
+    c["rank"] = args.cpu_rank or c["rank"]
+    c["batch"] = args.cpu_batch or c["batch"]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    g = O.Geometry(embed_dim=cfg["embed_dim"], depth=cfg["depth"], num_heads=cfg["num_heads"], patch=cfg["patch"],
-                   num_classes=NUM_CLASSES, rank=cfg["rank"])
+    g = O.Geometry(embed_dim=c["embed_dim"], depth=c["depth"], num_heads=c["num_heads"], patch=c["patch"],
+                   num_classes=NUM_CLASSES, rank=c["rank"])
     st = O.synthetic_state(g)
-    bs = args.cpu_batch
-    x, y = O.synthetic_batch(g, bs)
+    x, y = O.synthetic_batch(g, c["batch"])
     opt = {}
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         O.train_step(st, opt, i + 1, g, x, y, 1.0, train=True, wdrop=0.1, drop_path=0.1)
         times.append(time.perf_counter() - t0)
-    best = min(times[warmup:])
-    return {"value": bs / best, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "%d timed steps (best of, after %d warm-up) of the same ViT-B/16 r16 train step at batch %d on "
-                      "the host CPU (oracle/cara_oracle.py: materialised deltas + weight dropout as the reference)"
-                      % (steps, warmup, bs), "sec_per_step": best}
+    timed = times[warmup:]
+    best = min(timed)
+    return {"value": c["batch"] / best, "unit": "images/s", "cores": threads, "torch_threads": torch.get_num_threads(),
+            "kind": "port",
+            "sample": "%d timed steps (best of, after %d warm-up) of the ViT-B/16 rank-%d fp32 train step at batch %d "
+                      "(BASELINE configs[0]) on the host CPU: oracle/cara_oracle.py = materialised deltas + weight "
+                      "dropout + autograd + AdamW as the reference's vit_cp.py:45-50"
+                      % (steps, warmup, c["rank"], c["batch"]),
+            "sec_per_step": best, "sec_per_step_mean": sum(timed) / len(timed), "steps": steps, "warmup": warmup,
+            "rank": c["rank"], "batch": c["batch"]}
 
 
 def run_reference(args):
+    """bench.py --impl reference: the CPU arm.  Always 1 warm-up + best of 3, whatever
+    --steps / --warmup ask for -- and the line reports the counts that were actually executed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=max(1, min(args.warmup, 1)))
+    base = cpu_reference(args, steps=3, warmup=1)
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": base["steps"], "warmup": base["warmup"],
+           "steps_requested": args.steps, "warmup_requested": args.warmup,
            "ms_per_step": base["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "ViT-B/16 CaRA rank=16 fine-tune step on the host CPU, batch %d sample" % args.cpu_batch,
-                      "config_key": args.config},
+           "config": {"workload": CPU_WORKLOAD, "config_key": "vitb16_r%d_cpu" % base["rank"],
+                      "batch": base["batch"], "gpu_arm_config_key": args.config},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -423,7 +441,8 @@ def main():
     ap.add_argument("--impl", default="cara_b200", choices=["cara_b200", "reference"])
     ap.add_argument("--config", default="vitb16_r16", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU baseline (default: BASELINE configs[0], 32)")
+    ap.add_argument("--cpu-rank", type=int, default=0, help="CP rank of the CPU baseline (default: BASELINE configs[0], 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weight-dropout", default="skip", choices=["skip", "exact"],
                     help="exact: the reference's nn.Dropout(0.1) on the materialised delta weights (slow path)")

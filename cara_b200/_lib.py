@@ -53,6 +53,8 @@ _SIGS = {
     "cara_merge_weights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cara_adamw_step": (C.c_int, [_P, _P, _P, _P, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_float, _P]),
+    "cara_adamw_step_dev": (C.c_int, [_P, _P, _P, _P, C.c_long, _P, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, _P]),
     "cara_sgemm": (C.c_int, [_P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P, C.c_int, C.c_int,
                              C.c_int, C.c_float, C.c_float, _P, C.c_long, _P]),
 }

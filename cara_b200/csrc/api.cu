@@ -139,6 +139,11 @@ int cara_adamw_step(float* p, const float* g, float* m, float* v, long n, float 
                     float eps, float weight_decay, int step, float gscale, void* stream) {
   CARA_RET(cara::adamw_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale, CARA_STREAM(stream)), "cara_adamw_step");
 }
+int cara_adamw_step_dev(float* p, const float* g, float* m, float* v, long n, float* state, float beta1, float beta2,
+                        float eps, float weight_decay, float gscale, void* stream) {
+  CARA_RET(cara::adamw_dev_launch(p, g, m, v, n, state, beta1, beta2, eps, weight_decay, gscale, CARA_STREAM(stream)),
+           "cara_adamw_step_dev");
+}
 int cara_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
                const float* bias, int M, int N, int K, float alpha, float beta, float* workspace, long workspace_floats,
                void* stream) {

@@ -104,6 +104,8 @@ int merge_launch(const float* W, const float* A, const float* Bf, const float* c
                  int slices, int R, cudaStream_t st);
 int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
                  float wd, int step, float gscale, cudaStream_t st);
+int adamw_dev_launch(float* p, const float* g, float* m, float* v, long n, float* state, float b1, float b2, float eps,
+                     float wd, float gscale, cudaStream_t st);
 int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc,
                  const float* bias, int M, int N, int K, float alpha, float beta, float* ws, long ws_floats,
                  cudaStream_t st);

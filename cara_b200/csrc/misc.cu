@@ -207,6 +207,47 @@ int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr,
   return cudaGetLastError() == cudaSuccess ? 0 : -68;
 }
 
+// Same update with the two per-step scalars read from DEVICE memory, so that the launch can sit inside a replayed CUDA
+// graph: state[0] = learning rate (written by the host, stream-ordered, whenever the schedule changes it),
+// state[1] = number of optimizer steps taken so far (advanced here), state[2] = exit ticket (int bits).
+// Every thread reads state[] before its block takes a ticket; the block that takes the last ticket is the only writer.
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long n, float* __restrict__ state, float b1, float b2, float eps,
+                                 float wd, float gscale) {
+  const float lr = *reinterpret_cast<volatile float*>(state);
+  const float step = *reinterpret_cast<volatile float*>(state + 1) + 1.0f;
+  const float bc1 = 1.0f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * mi / denom;
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int* ticket = reinterpret_cast<int*>(state + 2);
+    if (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1) {
+      *ticket = 0;
+      state[1] = step;
+      __threadfence();
+    }
+  }
+}
+int adamw_dev_launch(float* p, const float* g, float* m, float* v, long n, float* state, float b1, float b2, float eps,
+                     float wd, float gscale, cudaStream_t st) {
+  if (n <= 0 || state == nullptr) return -67;
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  adamw_dev_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, state, b1, b2, eps, wd, gscale);
+  return cudaGetLastError() == cudaSuccess ? 0 : -68;
+}
+
 // ---------------------------------------------------------------- fp32 SIMT GEMM with general strides
 // C[m,n] = alpha * sum_k A(m,k) B(k,n) + beta * C[m,n] + bias[n];  A(m,k) = A[m*ars + k*acs], B(k,n) = B[k*brs + n*bcs]
 __global__ void __launch_bounds__(256)

@@ -112,21 +112,9 @@ def ln_bwd(dh, x, mean, rstd, gamma, dx_in=None, rowscale=None, rows_per_sample=
     return dx_out, g_out
 
 
-def split_bf16(F):
-    """fp32 -> (hi, lo) bf16 with hi + lo ~= F to ~16 mantissa bits."""
-    hi = F.to(BF16)
-    return hi, (F - hi.float()).to(BF16)
-
-
 def factor_operands(F, Rp):
     """fp32 factor [..., rows, R] -> (ext bf16 [..., rows, 3Rp] = [hi|hi|lo], t2 bf16 [..., 2Rp, rows] = [hi^T; lo^T])."""
     F = F.detach().float().contiguous()
-    if not F.is_cuda:                     # host-side staging tests: the same arithmetic in torch
-        Fp = torch.nn.functional.pad(F, (0, Rp - F.shape[-1]))
-        hi, lo = split_bf16(Fp)
-        ext = torch.cat([hi, hi, lo], dim=-1).contiguous()
-        t2 = torch.cat([hi.transpose(-1, -2), lo.transpose(-1, -2)], dim=-2).contiguous()
-        return ext, t2
     st = _prep(F)
     rows, R = F.shape[-2], F.shape[-1]
     lead = tuple(F.shape[:-2])
@@ -250,14 +238,27 @@ def assemble_tokens(pe, cls, pos, B, N, Cc):
     return x
 
 
-def merge_weights(W, A, Bf, cs):
-    """W fp32 [N,K], A fp32 [K,R], Bf fp32 [N/S,R], cs fp32 [S,R] -> bf16 [N,K]."""
+_MERGE_RANKS = (4, 8, 16, 32)
+
+
+def merge_weights(W, A, Bf, cs, out=None):
+    """W fp32 [N,K], A fp32 [K,R], Bf fp32 [N/S,R], cs fp32 [S,R] -> bf16 [N,K] = W + sum_r (Bf (.) cs) A^T.
+    Any rank up to 32: the factors are zero-padded to the next rank the kernel is instantiated for."""
     st = _prep(W)
     N, K = W.shape
     S, R = cs.shape
-    out = torch.empty((N, K), device=W.device, dtype=BF16)
-    L.check(L.lib().cara_merge_weights(W.data_ptr(), A.contiguous().data_ptr(), Bf.contiguous().data_ptr(),
-                                       cs.contiguous().data_ptr(), out.data_ptr(), N, K, S, R, st), "cara_merge_weights")
+    Rk = next((r for r in _MERGE_RANKS if r >= R), None)
+    if Rk is None:
+        raise L.CaraLibraryError("cara_merge_weights: rank %d > %d is not supported" % (R, _MERGE_RANKS[-1]))
+    if Rk != R:
+        pad = lambda t: torch.nn.functional.pad(t, (0, Rk - R))                       # noqa: E731
+        A, Bf, cs = pad(A), pad(Bf), pad(cs)
+    A, Bf, cs = A.contiguous(), Bf.contiguous(), cs.contiguous()
+    assert W.dtype == F32 and W.is_contiguous() and A.dtype == F32 and Bf.dtype == F32 and cs.dtype == F32
+    if out is None:
+        out = torch.empty((N, K), device=W.device, dtype=BF16)
+    L.check(L.lib().cara_merge_weights(W.data_ptr(), A.data_ptr(), Bf.data_ptr(), cs.data_ptr(), out.data_ptr(),
+                                       N, K, S, Rk, st), "cara_merge_weights")
     return out
 
 
@@ -268,6 +269,18 @@ def adamw_step(p, g, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=
     assert p.dtype == F32 and p.is_contiguous() and g.is_contiguous()
     L.check(L.lib().cara_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0],
                                     betas[1], eps, weight_decay, step, gscale, st), "cara_adamw_step")
+
+
+def adamw_step_dev(p, g, m, v, state, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, gscale=1.0):
+    """AdamW with lr / step count read from the device tensor ``state`` (fp32[4], see cara_adamw_step_dev): the launch
+    is graph-capturable."""
+    global param_generation
+    param_generation += 1
+    st = _prep(p)
+    assert p.dtype == F32 and p.is_contiguous() and g.is_contiguous() and state.dtype == F32 and state.numel() >= 4
+    L.check(L.lib().cara_adamw_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                        state.data_ptr(), betas[0], betas[1], eps, weight_decay, gscale, st),
+            "cara_adamw_step_dev")
 
 
 _SGEMM_WS_FLOATS = 1 << 22          # 16 MB of split-K partial sums per device (stream-ordered reuse)

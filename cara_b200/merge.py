@@ -13,13 +13,17 @@ from . import ops, staging
 
 
 def _merged(lin, t):
-    W = lin.weight.detach().float().contiguous()
-    fz = ops.FrozenLinear.of(lin)
-    w = K.merge_weights(W, t.A.detach().contiguous(), t.B.detach().contiguous(), t.cs.detach().contiguous())
+    W = lin.weight.detach()
+    if W.dtype != torch.float32 or not W.is_contiguous():
+        W = W.float().contiguous()
     out = ops.FrozenLinear.__new__(ops.FrozenLinear)
-    out.w, out.wt = w, None          # inference only: no dX operand
-    out.bias = (t.bias.detach().float().contiguous() if t.bias is not None else fz.bias)
-    out.key = fz.key
+    out.w = K.merge_weights(W, t.A.detach(), t.B.detach(), t.cs.detach())
+    out.wt = None                    # inference only: no dX operand
+    if t.bias is not None:
+        out.bias = t.bias.detach().float().contiguous()
+    else:
+        out.bias = None if lin.bias is None else lin.bias.detach().float().contiguous()
+    out.key = ops.FrozenLinear.key_of(lin)
     return out
 
 

@@ -27,14 +27,17 @@ class FrozenLinear:
         self.w = w.to(BF16).contiguous()
         self.wt = w.t().to(BF16).contiguous()
         self.bias = None if lin.bias is None else lin.bias.detach().to(F32).contiguous()
-        self.key = (lin.weight.data_ptr(), lin.weight._version, lin.weight.device,
-                    None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
+        self.key = FrozenLinear.key_of(lin)
+
+    @staticmethod
+    def key_of(lin):
+        return (lin.weight.data_ptr(), lin.weight._version, lin.weight.device,
+                None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
 
     @staticmethod
     def of(lin):
         fz = lin.__dict__.get("_cara_frozen")
-        key = (lin.weight.data_ptr(), lin.weight._version, lin.weight.device,
-               None if lin.bias is None else (lin.bias.data_ptr(), lin.bias._version))
+        key = FrozenLinear.key_of(lin)
         if fz is None or fz.key != key:
             fz = FrozenLinear(lin)
             lin.__dict__["_cara_frozen"] = fz

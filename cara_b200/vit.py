@@ -400,9 +400,11 @@ def load_npz_weights(model, checkpoint_path, prefix=""):
     return model
 
 
-def create_model(model_name, pretrained=False, checkpoint_path="", **kwargs):
+def create_model(model_name, pretrained=False, checkpoint_path="", allow_missing_checkpoint=False, **kwargs):
     """``timm.models.create_model`` for the ViT names the reference uses.  ``checkpoint_path``: a JAX ``.npz``
-    (vit_cp.py:155, imported by ``load_npz_weights``) or a torch state_dict file."""
+    (vit_cp.py:155, imported by ``load_npz_weights``) or a torch state_dict file.  A missing checkpoint raises, as timm
+    does -- fine-tuning a randomly initialised backbone by accident is worse than stopping; synthetic runs (bench,
+    tests, ``vit_cp.py --synthetic``) pass ``allow_missing_checkpoint=True`` and keep the random initialisation."""
     if model_name not in _GEOMETRY:
         raise RuntimeError("Unknown model (%s)" % model_name)
     if pretrained:
@@ -411,15 +413,15 @@ def create_model(model_name, pretrained=False, checkpoint_path="", **kwargs):
     cfg.update(kwargs)
     model = VisionTransformer(**cfg)
     if checkpoint_path:
-        if str(checkpoint_path).lower().endswith((".npz", ".npy")):
-            import os
+        import os
+        if not os.path.exists(checkpoint_path):
+            if not allow_missing_checkpoint:
+                raise FileNotFoundError("checkpoint %r not found (pass allow_missing_checkpoint=True / "
+                                        "--allow-random-init to keep random-init weights)" % (checkpoint_path,))
             import warnings
-            if os.path.exists(checkpoint_path):
-                load_npz_weights(model, checkpoint_path)
-            else:
-                # the reference's entry point hard-codes ./ViT-B_16.npz (vit_cp.py:155); without the file (no
-                # network here) the synthetic runs keep the random initialisation
-                warnings.warn("checkpoint %r not found: keeping random-init weights" % (checkpoint_path,))
+            warnings.warn("checkpoint %r not found: keeping random-init weights" % (checkpoint_path,))
+        elif str(checkpoint_path).lower().endswith((".npz", ".npy")):
+            load_npz_weights(model, checkpoint_path)
         else:
             model.load_state_dict(torch.load(checkpoint_path, map_location="cpu"), strict=False)
     return model

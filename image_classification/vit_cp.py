@@ -9,7 +9,8 @@ its loop body (vit_cp.py:45-50): forward, cross-entropy, backward, AdamW(lr, wd=
 cosine schedule stepped with the epoch index (vit_cp.py:55-56,187), test every 10 epochs and keep the best
 checkpoint (vit_cp.py:57-68).  Additive flags: ``--epochs``, ``--batch-size``, ``--synthetic`` (VTAB-shaped
 random data when ./data/vtab-1k is absent), ``--no-merge`` (evaluate through the adapter kernels instead of
-folding the CP delta into the frozen weights first).  Multi-GPU: launch with torchrun; the batch is sharded
+folding the CP delta into the frozen weights first), ``--weight-dropout exact|skip`` (default exact = the
+reference's train-mode dropout on the materialised delta), ``--retrain-mode``, ``--allow-random-init``.  Multi-GPU: launch with torchrun; the batch is sharded
 over the ranks and only the flat CP+head gradient (<= 1.1 MB) is all-reduced.
 """
 import os
@@ -27,6 +28,7 @@ from vtab_config import config  # noqa: E402
 from cara_b200 import train as T  # noqa: E402
 from cara_b200.merge import merge_cara  # noqa: E402
 from cara_b200.vit import create_model  # noqa: E402
+from cara_b200.wdrop import set_weight_dropout  # noqa: E402
 from src.cara.cara import cara  # noqa: E402
 
 
@@ -43,12 +45,18 @@ def test(model, dl):
 
 
 def train(args, model, dl, tdl, opt, epochs, world_size=1, rank=0):
-    """Reference vit_cp.py:19-70."""
+    """Reference vit_cp.py:19-70, including two things that are easy to miss: the learning rate of each step
+    (T.EpochCosineSchedule: epoch 0 runs at warmup_lr_init = 1e-6, the scheduler is stepped after opt.step()), and the
+    fact that ``test()`` leaves the model in eval mode (vit_cp.py:75) and the loop never calls ``model.train()`` again
+    -- from the first periodic test (epoch 10) on, the reference trains WITHOUT weight dropout and DropPath.
+    ``--retrain-mode`` restores train mode after every test instead."""
     model.train()
-    acc, old_name, use_sched = 0.0, None, True
+    acc, old_name = 0.0, None
+    sched = T.EpochCosineSchedule(base_lr=args.lr)
+    opt.param_groups[0]["lr"] = sched.lr
     # The loader drops the last partial batch (vtab.py:84-88), so every step has the same shape: zero_grad + forward +
-    # CE + backward are captured once into a CUDA graph and replayed (at the reference's batch of 64 the ~470 launches
-    # of a step take longer to enqueue from Python than to run).
+    # CE + backward (+ the gradient all-reduce and AdamW) are captured once into a CUDA graph and replayed (at the
+    # reference's batch of 64 the launches of a step take longer to enqueue from Python than to run).
     step = None
     for epoch in range(epochs):
         for x, y in dl:
@@ -59,15 +67,15 @@ def train(args, model, dl, tdl, opt, epochs, world_size=1, rank=0):
             if step is None and not args.no_graph:
                 step = T.GraphedStep(model, opt, x, y, world_size)
             loss = step(x, y) if step is not None else T.train_step(model, opt, x, y, world_size)
-            if use_sched:
-                opt.param_groups[0]["lr"] = T.cosine_lr(epoch, base_lr=args.lr)
+            opt.param_groups[0]["lr"] = sched.after_step(epoch)
         if rank == 0:
             print(f"e: {epoch}, l: {round(float(loss), 7)}, a:{acc}", flush=True)
         if epoch % 10 == 0 and epoch != 0:
-            if epoch >= 50:
-                use_sched = False
+            sched.after_test(epoch)
             acc = test(model, tdl)
-            model.train()
+            if args.retrain_mode:
+                model.train()
+            step = None                       # the mode (dropout / DropPath kernels) is baked into the captured graph
             if acc > args.best_acc and rank == 0:
                 args.best_acc = acc
                 if old_name is not None:
@@ -77,7 +85,29 @@ def train(args, model, dl, tdl, opt, epochs, world_size=1, rank=0):
     return model, old_name
 
 
-def _parse_args():
+def build_model(args, data_config, num_classes):
+    """vit_cp.py:155-166 of the reference: backbone (+ ./ViT-B_16.npz), cara(), fresh classifier, on the GPU."""
+    vit = create_model(args.model, checkpoint_path="./ViT-B_16.npz", drop_path_rate=0.1,
+                       allow_missing_checkpoint=args.synthetic or args.allow_random_init)
+    vit = cara({"model": vit, "rank": args.dim, "scale": data_config["scale"], "l_mu": data_config["init_mean"],
+                "l_std": data_config["init_std"]})
+    vit.reset_classifier(num_classes)
+    vit = vit.cuda()
+    set_weight_dropout(vit, args.weight_dropout)
+    return vit
+
+
+def load_for_evaluate(vit, path, merge=True):
+    """The ``--evaluate`` branch (reference vit_cp.py:168-173): load a fine-tuned state_dict (the reference's own
+    ``th.save(vit.state_dict())`` files load as they are: same 164 keys, nn.Linear [out,in] layout) and, unless
+    ``--no-merge``, fold the CP delta into the frozen weights once with the reconstruction kernel."""
+    vit.load_state_dict(th.load(path, map_location="cuda"))
+    if merge:
+        merge_cara(vit)
+    return vit
+
+
+def _parse_args(argv=None):
     p = ArgumentParser(formatter_class=ArgumentDefaultsHelpFormatter)
     p.add_argument("--dim", default=32, type=int, help="Number of trainable ranks.")
     p.add_argument("--lr", default=1e-3, type=float, help="Learning rate")
@@ -89,9 +119,16 @@ def _parse_args():
     p.add_argument("--synthetic", action="store_true", help="force VTAB-shaped synthetic data")
     p.add_argument("--no-merge", action="store_true", help="evaluate without folding the CP delta into W")
     p.add_argument("--no-graph", action="store_true", help="enqueue every train step eagerly (no CUDA graph replay)")
+    p.add_argument("--weight-dropout", default="exact", choices=["exact", "skip"],
+                   help="exact: nn.Dropout(0.1) on the materialised CP delta in train mode, as the reference "
+                        "(cara.py:35,57,81,92; slow path, cara_b200.wdrop); skip: fused fast path without it")
+    p.add_argument("--retrain-mode", action="store_true",
+                   help="call model.train() after each periodic test (the reference stays in eval mode, vit_cp.py:75)")
+    p.add_argument("--allow-random-init", action="store_true",
+                   help="keep the random initialisation when ./ViT-B_16.npz is missing (implied by --synthetic)")
     p.add_argument("--gpu-preprocess", action="store_true",
                    help="decode on the CPU, resize + normalise on the GPU (bit-identical to the reference's transforms)")
-    return p.parse_args()
+    return p.parse_args(argv)
 
 
 def main(sd=None):
@@ -116,18 +153,11 @@ def main(sd=None):
 
     train_dl, test_dl = get_data(name, evaluate=True, batch_size=args.batch_size,
                                  synthetic=True if args.synthetic else None, gpu_preprocess=args.gpu_preprocess)
-    num_classes = get_classes_num(name)
-    vit = create_model(args.model, checkpoint_path="./ViT-B_16.npz", drop_path_rate=0.1)
-    vit = cara({"model": vit, "rank": args.dim, "scale": scale, "l_mu": data_config["init_mean"],
-                "l_std": data_config["init_std"]})
-    vit.reset_classifier(num_classes)
-    vit = vit.cuda()
+    vit = build_model(args, data_config, get_classes_num(name))
 
     if args.evaluate is not None:
         print("Only evaluation")
-        vit.load_state_dict(th.load(args.evaluate, map_location="cuda"))
-        if not args.no_merge:
-            merge_cara(vit)
+        load_for_evaluate(vit, args.evaluate, merge=not args.no_merge)
         acc = test(vit, test_dl)
         print(f"Accuracy: {acc}")
         sys.exit(0)

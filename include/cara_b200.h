@@ -150,6 +150,14 @@ CARA_API int cara_merge_weights(const float* W, const float* A, const float* Bf,
 CARA_API int cara_adamw_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int step, float gscale, void* stream);
 
+/* The same update with its two per-step scalars in DEVICE memory, so that the launch can be part of a replayed CUDA
+ * graph (the whole vit_cp.py:45-50 iteration -- zero_grad, forward, CE, backward, gradient all-reduce, AdamW -- is then
+ * one graph launch): state is fp32[4] = { learning rate, optimizer steps taken so far, exit ticket (zero), unused }.
+ * The kernel uses step = state[1] + 1 for the bias corrections and stores it back; the host rewrites state[0]
+ * (stream-ordered) whenever the schedule changes the rate (vit_cp.py:55-56). */
+CARA_API int cara_adamw_step_dev(float* p, const float* g, float* m, float* v, long n, float* state, float beta1,
+                                 float beta2, float eps, float weight_decay, float gscale, void* stream);
+
 /* Plain fp32 GEMM with general strides for the tiny trainable head (vit_cp.py:166):
  *   C[m,n] = alpha * sum_k A[m*ars + k*acs] * B[k*brs + n*bcs] + beta * C[m,n] + bias[n].
  * workspace (optional, device, workspace_floats fp32 elements, borrowed for the call): lets small problems split K

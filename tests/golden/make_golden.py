@@ -26,16 +26,24 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+import importlib.util  # noqa: E402
+
+REF_CARA = "/root/reference/src/cara/cara.py"
 sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
-sys.path.insert(0, "/root/reference")
 sys.path.insert(0, ROOT)
 
 from timm.models import create_model  # noqa: E402  (the shim)
-from src.cara import cara as ref_cara  # noqa: E402  (the unmodified reference module)
+
+# The repo's own ``src`` package shadows the reference's ``src`` namespace package on sys.path, so the unmodified
+# reference module is loaded by FILE PATH (under a private module name; it only imports torch / timm / tensorly).
+_spec = importlib.util.spec_from_file_location("_reference_cara", REF_CARA)
+ref_cara = importlib.util.module_from_spec(_spec)
+sys.modules["_reference_cara"] = ref_cara
+_spec.loader.exec_module(ref_cara)
 
 from oracle import cara_oracle as O  # noqa: E402  (inputs only)
 
-assert ref_cara.__file__.startswith("/root/reference/"), ref_cara.__file__
+assert os.path.realpath(ref_cara.__file__) == REF_CARA, ref_cara.__file__
 
 
 def build_reference(g: O.Geometry, scale: float, dtype):
@@ -99,6 +107,9 @@ def run_halves(out):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:          # write somewhere else (e.g. to compare against the committed files)
+        HERE = os.path.abspath(sys.argv[1])
+        os.makedirs(HERE, exist_ok=True)
     torch.manual_seed(0)
     run_model(O.Geometry(depth=2, rank=8, num_classes=10), 2.5, torch.float64, 2, "ref_vitb_d2_r8_fp64.npz")
     run_model(O.Geometry(depth=12, rank=16, num_classes=100), 1.0, torch.float32, 2, "ref_vitb_d12_r16_fp32.npz")

@@ -36,10 +36,15 @@ def _small():
     return vit, st, g
 
 
-def test_staging_matches_oracle_factoring_and_grad_chain():
+def test_staging_matches_oracle_factoring_and_grad_chain(monkeypatch):
     """staged (A, cs, B, bias) == oracle.adapter_terms (A.1) and autograd through the staging reproduces the
-    oracle's chain rule to the CP parameters (A.2)."""
+    oracle's chain rule to the CP parameters (A.2).  The product's ``factor_operands`` is a CUDA kernel with no CPU
+    path; on this CPU-only run the test substitutes the torch formulation (tests/_torch_ref.py), which
+    test_factor_operands_kernel_matches_torch_formulation (-m gpu) holds bit-identical to the kernel."""
+    from cara_b200 import kernels as K
     from cara_b200 import staging
+    from tests import _torch_ref
+    monkeypatch.setattr(K, "factor_operands", _torch_ref.factor_operands)
     vit, st, g = _small()
     amap, mmap = staging.staged(vit)
     s = 2.5
@@ -102,6 +107,8 @@ def test_kernel_wrappers_refuse_cpu_tensors():
         K.gemm_cp(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(256, 64, dtype=torch.bfloat16))
     with pytest.raises(CaraLibraryError):
         K.ln_fwd(torch.zeros(8, 128), torch.ones(128), torch.zeros(128))
+    with pytest.raises(CaraLibraryError):
+        K.factor_operands(torch.zeros(8, 4), 16)
 
 
 def test_vtab_config_and_cli_surface():
@@ -157,3 +164,66 @@ def test_npz_checkpoint_import_roundtrip(tmp_path):
     assert dst2.head.weight.shape == (5, C) and dst2.pos_embed.shape == (1, 17, C)
     assert torch.equal(dst2.pos_embed[:, 0], src.pos_embed[:, 0])
     assert torch.equal(dst2.blocks[1].mlp.fc2.weight, src.blocks[1].mlp.fc2.weight)
+
+
+def test_cosine_lr_matches_timm_closed_form():
+    """cara_b200.train.cosine_lr against the closed form of timm 0.4.12's CosineLRScheduler._get_lr for the arguments
+    of vit_cp.py:187 (t_initial=100, warmup_t=10, lr_min=1e-5, warmup_lr_init=1e-6, decay_rate=0.1; t_mul 1, no warmup
+    prefix, cycle_limit 0), written out independently here."""
+    import math
+    from cara_b200 import train as T
+
+    def timm_lr(t, base=1e-3, t_initial=100, warmup_t=10, lr_min=1e-5, warmup_lr_init=1e-6, decay_rate=0.1):
+        if t < warmup_t:
+            return warmup_lr_init + t * ((base - warmup_lr_init) / warmup_t)
+        i = t // t_initial
+        t_curr = t - t_initial * i
+        gamma = decay_rate ** i
+        lo, hi = lr_min * gamma, base * gamma
+        return lo + 0.5 * (hi - lo) * (1 + math.cos(math.pi * t_curr / t_initial))
+
+    for base in (1e-3, 5e-4):
+        for t in range(0, 230):
+            assert T.cosine_lr(t, base_lr=base) == pytest.approx(timm_lr(t, base=base), rel=1e-12, abs=0), (t, base)
+    assert T.cosine_lr(0) == 1e-6 and T.cosine_lr(10) == pytest.approx(1e-5 + 0.5 * (1e-3 - 1e-5) * (1 + math.cos(0.1 * math.pi)))
+    assert T.cosine_lr(9) == pytest.approx(1e-6 + 9 * (1e-3 - 1e-6) / 10)
+
+
+def test_per_step_lr_sequence_of_the_reference_loop():
+    """The learning rate of EVERY optimizer step of reference vit_cp.py:26-59: the scheduler leaves warmup_lr_init in the
+    optimizer at construction and is stepped AFTER opt.step(), so batch 0 of epoch e runs at the rate of epoch e-1; it is
+    dropped at the periodic test of epoch 50.  Simulated here with the reference's control flow and compared with
+    cara_b200.train.EpochCosineSchedule as image_classification/vit_cp.py drives it."""
+    from cara_b200 import train as T
+    batches = 3
+    # the reference's control flow, literally
+    want, lr, sched_on = [], T.cosine_lr(0), True
+    for epoch in range(100):
+        for _ in range(batches):
+            want.append(lr)                              # opt.step() uses the current rate
+            if sched_on:
+                lr = T.cosine_lr(epoch)                  # sched.step(epoch)
+        if epoch % 10 == 0 and epoch != 0 and epoch >= 50:
+            sched_on = False
+    got, s = [], T.EpochCosineSchedule(base_lr=1e-3)
+    cur = s.lr
+    for epoch in range(100):
+        for _ in range(batches):
+            got.append(cur)
+            cur = s.after_step(epoch)
+        if epoch % 10 == 0 and epoch != 0:
+            s.after_test(epoch)
+    assert got == want
+    assert got[0] == got[batches - 1] == 1e-6                     # all of epoch 0 at warmup_lr_init
+    assert got[batches] == 1e-6 and got[batches + 1] == pytest.approx(1e-6 + (1e-3 - 1e-6) / 10)
+    assert got[-1] == T.cosine_lr(50) and got[51 * batches + 1] == T.cosine_lr(50)   # frozen after epoch 50's test
+
+
+def test_create_model_raises_on_missing_checkpoint(tmp_path):
+    from cara_b200.vit import create_model
+    missing = os.path.join(str(tmp_path), "ViT-B_16.npz")
+    with pytest.raises(FileNotFoundError):
+        create_model("vit_base_patch16_224_in21k", checkpoint_path=missing, depth=1, embed_dim=128, num_heads=2)
+    with pytest.warns(UserWarning):
+        create_model("vit_base_patch16_224_in21k", checkpoint_path=missing, allow_missing_checkpoint=True, depth=1,
+                     embed_dim=128, num_heads=2)
