@@ -33,17 +33,37 @@ CONFIGS = {
 }
 NUM_CLASSES = 100
 METRIC = "fine-tune images/sec, ViT-B/16 CaRA r16, 1/2/4/8 B200; fused GEMM % TC peak"
+METRICS = {"vitb16_r16": METRIC,
+           "vitl16_r32": "fine-tune images/sec, ViT-L/16 CaRA r32 data-parallel (BASELINE configs[2])",
+           "vith14_r32": "fine-tune images/sec, ViT-H/14 CaRA r32 data-parallel, 257 tokens (BASELINE configs[3])"}
+WORKLOADS = {
+    "vitb16_r16": "ViT-B/16 CaRA rank=16 bf16 fine-tune step (fwd + CE + dX-only bwd + factor grads + AdamW over "
+                  "CP*+head), batch 256 per GPU, 224x224, 100 classes, random-init weights",
+    "vitl16_r32": "ViT-L/16 CaRA rank=32 bf16 data-parallel fine-tune step, 224x224, 100 classes, random-init weights",
+    "vith14_r32": "ViT-H/14 CaRA rank=32 bf16 data-parallel fine-tune step, 224x224 (257 tokens), 100 classes, "
+                  "random-init weights"}
 
 
 def gemm_traffic(config_key):
     """DRAM bytes per gemm_cp_kernel launch (launch-weighted over one step) from the committed ncu --set full
     captures (profiles/r01_traffic.json); None when no capture exists for this configuration."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
         d = json.load(open(p))
         if d.get("config_key") == config_key:
             return float(d["avg_dram_bytes_per_launch"])
     return None
+
+
+def gemm_ncu(config_key):
+    """Second denominator for the GEMM roofline: ncu's sm__pipe_tensor_cycles_active, time-weighted over the
+    fused-projection shapes of one step, from the newest committed capture (profiles/rNN_traffic.json)."""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        d = json.load(open(p))
+        if d.get("config_key") == config_key and "tensor_pipe_pct_time_weighted" in d:
+            return {"tensor_pipe_pct_time_weighted": d["tensor_pipe_pct_time_weighted"], "source": os.path.basename(p)}
+    return {}
 
 
 def peaks():
@@ -157,6 +177,15 @@ def run_cuda(args):
     _install_init_module()
     cfg = CONFIGS[args.config]
     B = args.batch or cfg["batch"]
+    strong = args.global_batch > 0
+    if strong:                                   # strong scaling (BASELINE configs[2]): the GLOBAL batch is fixed
+        if args.global_batch % world != 0:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        B = args.global_batch // world
+        if args.accum == 0:                      # activations are kept for one micro-batch of the config's batch size
+            args.accum = max(1, B // cfg["batch"])
+    if args.accum == 0:
+        args.accum = 1
     vit, opt = build_model(cfg, dev)
     apply_weight_dropout(vit, args.weight_dropout)
     if cfg.get("eval"):
@@ -263,20 +292,21 @@ def run_cuda(args):
         ms, ms_e2e, gemm_ms = [float(v) for v in t]
     total_images = B * world * args.steps
     peak_tf, peak_hbm, peak_src = peaks()
+    ncu = gemm_ncu(args.config)
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     out = {
-        "metric": METRIC, "value": total_images / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "metric": METRICS[args.config], "value": total_images / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 CaRA rank=16 bf16 fine-tune step (fwd + CE + dX-only bwd + factor grads + "
-                               "AdamW over CP*+head), batch 256 per GPU, 224x224, 100 classes, random-init weights"
-                   if args.config == "vitb16_r16" else args.config,
-                   "config_key": args.config, "batch_per_gpu": B, "global_batch": B * world, "tokens": 197,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config],
+                   "config_key": args.config, "batch_per_gpu": B, "global_batch": B * world,
+                   "tokens": (224 // cfg["patch"]) ** 2 + 1,
                    "parallelism": "dp%d" % world, "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2",
                    "drop_path": 0.1,
                    "weight_dropout": "not applied (documented deviation; --weight-dropout exact selects the slow path)"
                    if args.weight_dropout == "skip" else "exact (reference semantics: 3 GEMMs per projection)",
                    "cuda_graph": not args.no_graph, "micro_batches": args.accum,
+                   "update_in_graph": bool(getattr(step, "capture_update", False)),
                    "algorithmic_gflop_per_image": cfg["gflop_per_image"]},
         "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 8), "d2h_bytes_per_step": 4,
@@ -285,9 +315,13 @@ def run_cuda(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_cp_kernel (fused CP projections fwd + dX, %d launches over 2 eagerly enqueued steps)" % len(gemm_events),
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": gemm_traffic(args.config), "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json)",
+                     "traffic": gemm_traffic(args.config), "traffic_unit": "DRAM bytes per launch (ncu --set full, newest profiles/rNN_traffic.json)",
                      "algorithmic_flops_per_launch": gemm_flops / max(1, len(gemm_events)),
                      "peak_source": peak_src,
+                     "timing": "CUDA events around each launch of two eagerly enqueued steps right after the timed loop "
+                               "(nodes of a replayed graph cannot be timed individually)",
+                     "ncu_tensor_pipe_pct": ncu.get("tensor_pipe_pct_time_weighted"),
+                     "ncu_source": ncu.get("source"),
                      "step_frac_of_peak": cfg["gflop_per_image"] * 1e9 * B / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
         "loss": loss_value,
     }
@@ -308,8 +342,10 @@ def run_eval(args, cfg, vit, dev, world, rank):
     from cara_b200.merge import merge_cara
     B = args.batch or cfg["batch"]
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    merged = merge_cara(vit)                     # first call: module loading, allocator growth
+    torch.cuda.synchronize()
     t0.record()
-    merged = merge_cara(vit)
+    merged = merge_cara(vit)                     # timed: 4 x depth reconstruction-kernel launches + their staging
     t1.record()
     torch.cuda.synchronize()
     merge_ms = t0.elapsed_time(t1)
@@ -340,10 +376,26 @@ def run_eval(args, cfg, vit, dev, world, rank):
     launches = K.launch_count - launches0
     stage = [torch.empty_like(dev_x[0]) for _ in range(2)]
     pred_host = torch.zeros(B, dtype=torch.int64).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):                               # H2D of batch i on the copy stream, overlapping forward i-1
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[s])
+            stage[s].copy_(host_x[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
     t0.record()
+    prefetch(0)
     for i in range(args.steps):
-        stage[i % 2].copy_(host_x[i % 2], non_blocking=True)
-        pred_host.copy_(fwd(stage[i % 2]), non_blocking=True)
+        s = i % 2
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[s])
+        pred_host.copy_(fwd(stage[s]), non_blocking=True)
+        done[s].record()
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -446,8 +498,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weight-dropout", default="skip", choices=["skip", "exact"],
                     help="exact: the reference's nn.Dropout(0.1) on the materialised delta weights (slow path)")
-    ap.add_argument("--accum", type=int, default=1,
-                    help="micro-batches per optimizer step (the per-GPU batch is split; activations kept for one)")
+    ap.add_argument("--accum", type=int, default=0,
+                    help="micro-batches per optimizer step (the per-GPU batch is split; activations kept for one); "
+                         "default 1, or per-GPU batch / config batch with --global-batch")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fix the GLOBAL batch (BASELINE configs[2]: 2048) and split it over the GPUs")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

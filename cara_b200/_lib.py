@@ -10,6 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcara_b200.so")
 
 EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+SIDE_NONE, SIDE_FWD, SIDE_BWD = 0, 1, 2
+SYNC_WORDS = 16386
+ABI_VERSION = 2
 
 
 class GemmDesc(C.Structure):
@@ -24,7 +27,12 @@ class GemmDesc(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int),
         ("out2", C.c_void_p), ("ldo2", C.c_int),
         ("aux", C.c_void_p), ("ldaux", C.c_int),
-        ("epi", C.c_int), ("num_sms", C.c_int), ("pair", C.c_int),
+        ("epi", C.c_int), ("num_sms", C.c_int),
+        ("side", C.c_int), ("side_rp", C.c_int), ("side_slices", C.c_int),
+        ("P", C.c_void_p), ("ldp", C.c_long),
+        ("side_scales", C.c_void_p), ("side_T", C.c_void_p),
+        ("side_U", C.c_void_p), ("side_ldu", C.c_long),
+        ("side_dc", C.c_void_p), ("sync_ws", C.c_void_p),
     ]
 
 

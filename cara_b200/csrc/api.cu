@@ -43,7 +43,12 @@ int cara_gemm_cp(const cara_gemm_desc* d, void* stream) {
   g.out = static_cast<__nv_bfloat16*>(d->out); g.ldo = d->ldo;
   g.out2 = static_cast<__nv_bfloat16*>(d->out2); g.ldo2 = d->ldo2;
   g.aux = static_cast<const __nv_bfloat16*>(d->aux); g.ldaux = d->ldaux;
-  g.epi = d->epi; g.num_sms = d->num_sms; g.pair = d->pair;
+  g.epi = d->epi; g.num_sms = d->num_sms;
+  g.side = d->side; g.side_rp = d->side_rp; g.side_slices = d->side_slices;
+  g.P = static_cast<const __nv_bfloat16*>(d->P); g.ldp = d->ldp;
+  g.side_scales = d->side_scales; g.side_T = d->side_T;
+  g.side_U = static_cast<__nv_bfloat16*>(d->side_U); g.side_ldu = d->side_ldu;
+  g.side_dc = d->side_dc; g.sync = static_cast<unsigned*>(d->sync_ws);
   int rc = cara::gemm_cp_launch(g, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(rc, "cara_gemm_cp: launch failed / bad arguments");
   return 0;

@@ -7,6 +7,10 @@
 namespace cara {
 
 enum GemmEpilogue { EPI_NONE = 0, EPI_GELU = 1, EPI_DGELU = 2 };
+enum GemmSide { SIDE_NONE = 0, SIDE_FWD = 1, SIDE_BWD = 2 };
+
+constexpr int kSyncPanels = 4096;                // M <= 524,288 rows
+constexpr int kSyncWords = 2 + 4 * kSyncPanels;  // generation, exit ticket, one flag per (128-row panel, TMEM lane group)
 
 // Device-side arguments (passed by value).
 struct GemmArgs {
@@ -20,7 +24,18 @@ struct GemmArgs {
   __nv_bfloat16* out; int ldo;
   __nv_bfloat16* out2; int ldo2;
   const __nv_bfloat16* aux; int ldaux;
-  int debug;          // experiments (CARA_GEMM_DEBUG): 1 = epilogue only drains TMEM, 2 = no TMA loads / no full-barrier waits
+  int debug;          // experiments (CARA_GEMM_DEBUG): 1 = epilogue only drains TMEM, 4 = no output staging, 8 = cheap GELU
+  // rank-R side tiles (one per 128-row panel, ahead of the panel's output tiles; see gemm_sm100.cu)
+  int side;             // GemmSide
+  int side_rp;          // padded rank (16 / 32); the side MMA has N = 2 * side_rp columns ([hi ; lo] rows of the factor)
+  int side_slices;      // SIDE_FWD: output slices of Uhat; SIDE_BWD: K-slices of A0 (one dU accumulator each)
+  int side_kb_slice;    // k-blocks per K-slice (SIDE_FWD: kblocks_main)
+  int side_la;          // panels of lookahead between a side tile and its consumers (>= one round of the grid)
+  const float* side_scales;            // [side_slices, side_rp] fp32
+  float* side_T;                       // [M, side_rp] fp32: SIDE_FWD out (may be null), SIDE_BWD in
+  __nv_bfloat16* side_U; long side_ldu;// SIDE_FWD: Uhat [M, slices * 3rp]; SIDE_BWD: dThat [M, 3rp]  ([hi | lo | hi])
+  float* side_dc;                      // SIDE_BWD: [side_slices, side_rp] fp32, accumulated
+  unsigned* sync;                      // kSyncWords device words, zero-initialised once by the caller
 };
 
 // Host-side problem description.
@@ -38,7 +53,15 @@ struct GemmDesc {
   const __nv_bfloat16* aux; int ldaux;
   int epi;
   int num_sms;
-  int pair;   // 1: CTA pairs (cta_group::2, 256 x 256 tiles); 0: single-CTA 128 x 256 tiles
+  // side tiles (optional): P = [2rp, K0 / (SIDE_BWD ? side_slices : 1)] bf16, rows [hi ; lo] of the transposed factor.
+  // With side != 0 and N == 0 only the side tiles run (the stand-alone rank-R row contraction).
+  int side; int side_rp; int side_slices;
+  const __nv_bfloat16* P; long ldp;
+  const float* side_scales;
+  float* side_T;
+  __nv_bfloat16* side_U; long side_ldu;
+  float* side_dc;
+  unsigned* sync;
 };
 
 int gemm_cp_launch(const GemmDesc& d, cudaStream_t st);

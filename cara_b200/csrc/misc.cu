@@ -214,10 +214,18 @@ int adamw_launch(float* p, const float* g, float* m, float* v, long n, float lr,
 __global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long n, float* __restrict__ state, float b1, float b2, float eps,
                                  float wd, float gscale) {
-  const float lr = *reinterpret_cast<volatile float*>(state);
-  const float step = *reinterpret_cast<volatile float*>(state + 1) + 1.0f;
-  const float bc1 = 1.0f - powf(b1, step);
-  const float bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+  // bias corrections in double by one thread per block (1 - b2^t for small t loses its digits in fast-math fp32)
+  __shared__ float s_hp[4];
+  if (threadIdx.x == 0) {
+    const float lr0 = *reinterpret_cast<volatile float*>(state);
+    const float t = *reinterpret_cast<volatile float*>(state + 1) + 1.0f;
+    s_hp[0] = lr0;
+    s_hp[1] = t;
+    s_hp[2] = static_cast<float>(1.0 - pow(static_cast<double>(b1), static_cast<double>(t)));
+    s_hp[3] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))));
+  }
+  __syncthreads();
+  const float lr = s_hp[0], step = s_hp[1], bc1 = s_hp[2], bc2_sqrt = s_hp[3];
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * gscale;

@@ -8,6 +8,9 @@
 // the two partial products are folded in fp32, and Uhat / dThat are emitted as [hi | lo | hi] column blocks so
 // that the tcgen05 GEMM's adapter segment computes hi*Bhi + lo*Bhi + hi*Blo against [Bhi | Bhi | Blo].
 //
+// (The row-wise contractions can also run as side tiles INSIDE the tcgen05 projection GEMM -- gemm_sm100.cu, opt-in:
+// measured slower in the step than these stand-alone passes, profiles/r02_side_tiles.md.)
+//
 //   rows_kernel (row-wise, K reduced):
 //     fwd : T = X A                     [M,Rp] fp32 (saved),  Uhat_s = cs_s (.) T   [M,S*3Rp] bf16 (hi|lo|hi)
 //     bwd : dU_s = G_s B  per slice s,  dThat = sum_s cs_s (.) dU_s  [M,3Rp] bf16 (hi|lo|hi),

@@ -13,7 +13,10 @@ from . import _lib as L
 BF16, F32 = torch.bfloat16, torch.float32
 launch_count = 0  # number of cara_* kernel launches issued (bench.py reports it as gpu_launches)
 param_generation = 0  # bumped by adamw_step: parameters changed behind autograd's version counters
-gemm_pair = int(__import__('os').environ.get('CARA_GEMM_PAIR', '0'))  # 1: experimental tcgen05 cta_group::2 tiles (slower so far)
+# CARA_SIDE_TILES=1: compute the rank-R row contractions (T = x A, dU = g B) as side tiles inside the projection GEMM's
+# launch instead of the stand-alone rows kernel.  Opt-in: correct (tests/test_kernels_gpu.py::test_gemm_side_tiles_*)
+# but measured slower in the step on B200 (profiles/r02_side_tiles.md).
+side_tiles = __import__("os").environ.get("CARA_SIDE_TILES", "0") == "1"
 gemm_events = None  # bench.py: list of (start event, end event, algorithmic flops) per fused-projection launch
 _dev = [None]
 
@@ -38,9 +41,49 @@ def round_rank(r):
     return 16 if r <= 16 else 32
 
 
+_sync_ws = {}
+
+
+def sync_workspace(device):
+    """The 16 KB of zero-initialised device words (generation counter + one flag per 128-row panel) the GEMM's side
+    tiles synchronise through; one per device, lent to every call (see include/cara_b200.h, sync_ws)."""
+    ws = _sync_ws.get(device)
+    if ws is None:
+        ws = _sync_ws[device] = torch.zeros(L.SYNC_WORDS, device=device, dtype=torch.int32)
+    return ws
+
+
+class Side:
+    """Side tiles of one fused projection (see cara_gemm_cp): the rank-R row contraction of the GEMM's own A0 rows.
+    ``mode`` L.SIDE_FWD: T = a0 P^T, Uhat = split(scales (.) T) -> ``U`` (the GEMM's a1), ``T`` saved (or None).
+    ``mode`` L.SIDE_BWD: dThat = split(sum_s scales[s] (.) (a0_s P^T)) -> ``U``, ``dc`` += sum_m dU_s (.) T."""
+    __slots__ = ("mode", "P", "scales", "T", "U", "dc")
+
+    def __init__(self, mode, P, scales, T, U, dc=None):
+        self.mode, self.P, self.scales, self.T, self.U, self.dc = mode, P, scales, T, U, dc
+
+
+def _fill_side(d, side, M, K0, device):
+    S, Rp = side.scales.shape
+    kslices = S if side.mode == L.SIDE_BWD else 1
+    assert side.P.dtype == BF16 and side.P.shape == (2 * Rp, K0 // kslices) and side.P.stride(1) == 1
+    assert side.scales.dtype == F32 and side.scales.is_contiguous()
+    assert side.U.dtype == BF16 and side.U.shape[0] == M and side.U.stride(1) == 1
+    assert side.U.shape[1] == (3 * Rp if side.mode == L.SIDE_BWD else S * 3 * Rp)
+    if side.T is not None:
+        assert side.T.dtype == F32 and side.T.shape == (M, Rp) and side.T.is_contiguous()
+    d.side, d.side_rp, d.side_slices = side.mode, Rp, S
+    d.P, d.ldp = side.P.data_ptr(), side.P.stride(0)
+    d.side_scales, d.side_T = side.scales.data_ptr(), _p(side.T)
+    d.side_U, d.side_ldu = side.U.data_ptr(), side.U.stride(0)
+    d.side_dc = _p(side.dc)
+    d.sync_ws = sync_workspace(device).data_ptr()
+
+
 def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, out=None, out2=None, aux=None,
-            want_pre=True, num_sms=0, pair=None):
-    """out[M,N] = a0[M,K0] b0[N,K0]^T + bias (+ adapter segment a1/b1), see cara_gemm_cp."""
+            want_pre=True, num_sms=0, side=None):
+    """out[M,N] = a0[M,K0] b0[N,K0]^T + bias (+ adapter segment a1/b1), see cara_gemm_cp.  ``side`` (a ``Side``):
+    the kernel also computes the low-rank operand -- then ``a1`` must be ``side.U``, which it fills before use."""
     st = _prep(a0)
     M, K0 = a0.shape
     N = b0.shape[0]
@@ -55,6 +98,9 @@ def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, o
         assert b1.shape[0] * ext_slices == N and a1.stride(1) == 1 and b1.stride(1) == 1
         d.K1, d.ext_slices = K1, ext_slices
         d.A1, d.lda1, d.B1, d.ldb1 = a1.data_ptr(), a1.stride(0), b1.data_ptr(), b1.stride(0)
+    if side is not None:
+        assert a1 is not None and a1.data_ptr() == side.U.data_ptr()
+        _fill_side(d, side, M, K0, a0.device)
     if bias is not None:
         assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
         d.bias = bias.data_ptr()
@@ -70,13 +116,14 @@ def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, o
         assert aux is not None and aux.dtype == BF16 and aux.shape == (M, N)
         d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
     d.epi, d.num_sms = epi, num_sms
-    d.pair = gemm_pair if pair is None else int(pair)
     if gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
         e1.record()
-        gemm_events.append((e0, e1, 2.0 * M * N * (K0 + (d.K1 // 3 if a1 is not None else 0))))
+        Rp = d.side_rp if side is not None else 0
+        # algorithmic flops: frozen product + adapter segment (rank Rp) + the side contraction (rank Rp)
+        gemm_events.append((e0, e1, 2.0 * M * N * (K0 + (d.K1 // 3 if a1 is not None else 0)) + 2.0 * M * K0 * Rp))
     else:
         L.check(L.lib().cara_gemm_cp(C.byref(d), st), "cara_gemm_cp")
     return (out, out2) if epi == L.EPI_GELU else out

@@ -100,11 +100,22 @@ class GradSink:
         return self.t["dA%d" % kind][..., :R], self.t["dcs%d" % kind][..., :R], self.t["dB%d" % kind][..., :R], db
 
 
-def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True):
+def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True, train=True):
+    """The frozen product + the adapter segment (cara.py:35,57,81,92 without the delta weight).  The rank-R row
+    contraction T = x A, Uhat_s = cs_s (.) T that feeds the segment runs as its own pass (default) or, with
+    CARA_SIDE_TILES=1, as side tiles of the same GEMM launch."""
     T = U = None
-    if ops is not None:
+    if ops is not None and not K.side_tiles:
+        # default: the row contraction T = x A, Uhat_s = cs_s (.) T as its own HBM-bound pass, then the GEMM
         T, U = K.adapter_rows_fwd(x, ops.a_t2, ops.cs_pad)
         y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_ext, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
+    elif ops is not None:
+        M = x.shape[0]
+        T = torch.empty((M, ops.rp), device=x.device, dtype=F32) if train else None
+        U = torch.empty((M, ops.slices * 3 * ops.rp), device=x.device, dtype=BF16)
+        side = K.Side(L.SIDE_FWD, ops.a_t2, ops.cs_pad, T, U)
+        y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_ext, ext_slices=ops.slices, epi=epi, want_pre=want_pre,
+                      side=side)
     else:
         y = K.gemm_cp(x, fz.w, bias=bias_eff, epi=epi, want_pre=want_pre)
     return y, T, U
@@ -129,12 +140,24 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink
         zs = torch.split(z, sizes)
         dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
         colsum = zs[3] if need_bias else None
-    # the three readers of G run back to back: for the C-wide projections G (77 MB at ViT-B) stays in the 126 MB L2
-    dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
+    if not K.side_tiles:
+        # the three readers of G run back to back: for the C-wide projections G (77 MB at ViT-B) stays in the 126 MB L2
+        dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
+        K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
+        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux) if need_dx else None
+        K.adapter_cols(x, dT, 1, Rp, out=dA)
+        if sink is not None:
+            return (dx,) + sink[0].release(sink[1], R, need_bias)
+        return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum
     K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
     dx = None
     if need_dx:
-        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux)
+        # dX GEMM; its side tiles contract the same G panels with B: dThat = sum_s cs_s (.) (G_s B), dcs += dU (.) T
+        dT = torch.empty((G.shape[0], 3 * Rp), device=G.device, dtype=BF16)
+        side = K.Side(L.SIDE_BWD, ops.b_t2, ops.cs_pad, T, dT, dcs)
+        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux, side=side)
+    else:
+        dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)      # the side tiles alone (first block's qkv)
     K.adapter_cols(x, dT, 1, Rp, out=dA)
     if sink is not None:
         return (dx,) + sink[0].release(sink[1], R, need_bias)
@@ -150,7 +173,7 @@ class CPLinearFunction(torch.autograd.Function):
         (GradSink, kind, layer): cs [L,S,R] and bias_eff [L,N] (and A [L,4C,R] for fc2) are the stacked terms of
         all layers -- autograd sees one gradient per kind instead of one per layer."""
         bias = bias_eff if (bias_eff is None or sink is None) else bias_eff[sink[2]]
-        y, T, U = _cp_linear_fwd(x, fz, bias if bias is not None else fz.bias, ops)
+        y, T, U = _cp_linear_fwd(x, fz, bias if bias is not None else fz.bias, ops, train=any(ctx.needs_input_grad))
         if sink is not None and any(ctx.needs_input_grad):
             sink[0].pending[sink[1]] += 1
         ctx.fz, ctx.ops, ctx.sink = fz, ops, sink
@@ -179,8 +202,8 @@ class CPMlpFunction(torch.autograd.Function):
                 sink1[0].pending[sink1[1]] += 1
                 sink2[0].pending[sink2[1]] += 1
         (u, g), T1, U1 = _cp_linear_fwd(x, fz1, bias1 if bias1 is not None else fz1.bias, ops1, epi=L.EPI_GELU,
-                                        want_pre=train)
-        y, T2, U2 = _cp_linear_fwd(g, fz2, bias2 if bias2 is not None else fz2.bias, ops2)
+                                        want_pre=train, train=train)
+        y, T2, U2 = _cp_linear_fwd(g, fz2, bias2 if bias2 is not None else fz2.bias, ops2, train=train)
         ctx.fz1, ctx.ops1, ctx.fz2, ctx.ops2 = fz1, ops1, fz2, ops2
         ctx.sink1, ctx.sink2 = sink1, sink2
         ctx.save_for_backward(x, u, g, T1, U1, T2, U2)

@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define CARA_B200_ABI_VERSION 1
+#define CARA_B200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define CARA_API __attribute__((visibility("default")))
 #else
@@ -37,7 +37,22 @@ CARA_API int cara_set_device(int device);
  * bf16 operands, fp32 accumulation in tensor memory, bf16 outputs.
  *   epi = CARA_EPI_GELU : out (may be NULL) = pre-activation, out2 = GELU(pre-activation)
  *   epi = CARA_EPI_DGELU: out = (.) * gelu'(aux[M,N])   (dX through the fc1 activation)
- * Requirements: K0 % 8 == 0, N % 64 == 0, K1 % 16 == 0, 16-byte aligned bases and row pitches. */
+ * Requirements: K0 % 8 == 0, N % 64 == 0, K1 % 16 == 0, 16-byte aligned bases and row pitches.
+ *
+ * Side tiles (side != 0): the low-rank operand A1 is itself a contraction of the SAME A0 rows with a [K0, R] factor
+ * (cara.py:35,57,81,92: x * delta_W = ((x A) (.) c) B^T), so the kernel computes it too, one extra tile per 128-row
+ * panel, from the A0 tiles the panel's output tiles are streaming anyway -- no second pass over x (or g) exists.
+ *   side = CARA_SIDE_FWD: T = A0 P^T (P = split(A)^T, bf16 [2*side_rp, K0] = [hi rows ; lo rows]);  side_T (optional,
+ *       fp32 [M, side_rp]) = T;  side_U[:, s*3rp : (s+1)*3rp] = split(side_scales[s] (.) T) for s < side_slices.
+ *   side = CARA_SIDE_BWD: dU_s = A0[:, s*w : (s+1)*w] P^T per K-slice s (w = K0 / side_slices, P bf16 [2*side_rp, w]);
+ *       side_U (bf16 [M, 3rp]) = split(sum_s side_scales[s] (.) dU_s);  side_dc[s] += sum_m dU_s (.) side_T  (fp32,
+ *       accumulated;  side_T is an INPUT here: the forward's T).
+ * With an adapter segment, side_U must be A1 (the kernel orders the segment's loads after the panel's side tile).
+ * N = 0 runs the side tiles alone.  side_rp in {16, 32}; side_slices <= 4; K0 % (64 * K-slices) == 0.
+ * sync_ws: CARA_SYNC_WORDS 32-bit words of device memory, zeroed ONCE by the caller and then lent to every call on the
+ * same stream (generation counter + four flags per panel; never cleared between calls or graph replays). */
+enum cara_side { CARA_SIDE_NONE = 0, CARA_SIDE_FWD = 1, CARA_SIDE_BWD = 2 };
+#define CARA_SYNC_WORDS 16386
 typedef struct cara_gemm_desc {
   int M, N, K0;
   const void* A0; long lda0;
@@ -51,7 +66,13 @@ typedef struct cara_gemm_desc {
   const void* aux; int ldaux;
   int epi;
   int num_sms; /* 0 = all */
-  int pair;    /* 0 = single-CTA 128x256 tiles (default); 1 = experimental CTA pairs (tcgen05 cta_group::2, 256x256 tiles) */
+  int side, side_rp, side_slices;
+  const void* P; long ldp;
+  const float* side_scales;
+  float* side_T;
+  void* side_U; long side_ldu;
+  float* side_dc;
+  void* sync_ws;
 } cara_gemm_desc;
 CARA_API int cara_gemm_cp(const cara_gemm_desc* d, void* stream);
 
@@ -75,7 +96,8 @@ CARA_API int cara_ln_bwd(const void* dh, const float* x, const float* mean, cons
  * an out-side factor laid out [hi | hi | lo].  Rp = rank zero-padded to 16 or 32.
  *
  * Forward:  T = X A (fp32 [M,Rp]);  Uhat[:, s*3Rp : (s+1)*3Rp] = split(scales[s] (.) T).
- * X bf16 [M,K] (K % 64 == 0); At2 = split(A)^T; scales fp32 [slices,Rp]. */
+ * X bf16 [M,K] (K % 64 == 0); At2 = split(A)^T; scales fp32 [slices,Rp].
+ * (cara_gemm_cp can compute the same quantities as side tiles of the projection launch, see there.) */
 CARA_API int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At2, const float* scales,
                                    int slices, int Rp, float* T, void* Uhat, void* stream);
 /* Backward of the same chain: per output slice s, dU_s = G[:, s*w:(s+1)*w] B;

@@ -21,7 +21,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(L.exported_symbols()) == declared
-    assert L.lib().cara_abi_version() == 1
+    assert L.lib().cara_abi_version() == L.ABI_VERSION
 
 
 def _small():

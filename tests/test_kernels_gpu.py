@@ -202,6 +202,85 @@ def test_adapter_cols(K, M, Kc, R, S):
     assert rel(cs, X.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K0,R,S,epi", [
+    (1000, 768, 768, 16, 1, 0), (777, 2304, 768, 8, 3, 0), (640, 3072, 1024, 32, 4, 1), (515, 1024, 4096, 32, 1, 0),
+    (128, 256, 64, 16, 1, 0),                                   # a single panel, a single k-block
+    (50432, 2304, 768, 16, 3, 0), (50432, 3072, 768, 16, 4, 1), (50432, 768, 3072, 16, 1, 0)])   # the bench shapes
+def test_gemm_side_tiles_forward(K, M, N, K0, R, S, epi):
+    """The fused projection with its side tiles: ONE launch computes T = x A, Uhat_s = cs_s (.) T (side tiles) and
+    y = x W^T + b + Uhat B^T (output tiles reading the side tiles' rows behind the per-panel flags).  Checked against
+    fp64 torch for T / Uhat and fp32 torch for y -- twice in a row (the generation counter must advance)."""
+    from cara_b200 import _lib as L
+    Rp = K.round_rank(R)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = (torch.randn(M, K0, device="cuda", generator=g) * 0.5).to(BF16)
+    W = (torch.randn(N, K0, device="cuda", generator=g) * 0.05).to(BF16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    A = torch.randn(K0, R, device="cuda", generator=g) * 0.1
+    Bf = torch.randn(N // S, R, device="cuda", generator=g) * 0.2
+    cs = torch.zeros(S, Rp, device="cuda"); cs[:, :R] = torch.randn(S, R, device="cuda", generator=g)
+    _, a_t2 = K.factor_operands(A, Rp)
+    b_ext, _ = K.factor_operands(Bf, Rp)
+    Tref = torch.nn.functional.pad(x.double() @ A.double(), (0, Rp - R)).float()
+    Uref = torch.cat([Tref * cs[s] for s in range(S)], 1)
+    w = N // S
+    ref = x.float() @ W.float().T + bias
+    for s in range(S):
+        ref[:, s * w:(s + 1) * w] += (Tref[:, :R] * cs[s, :R]) @ Bf.T
+    for _ in range(2):
+        T = torch.full((M, Rp), float("nan"), device="cuda")
+        U = torch.full((M, S * 3 * Rp), float("nan"), device="cuda", dtype=BF16)
+        side = K.Side(L.SIDE_FWD, a_t2, cs, T, U)
+        out = K.gemm_cp(x, W, bias=bias, a1=U, b1=b_ext, ext_slices=S, epi=epi, side=side)
+        y = out[0] if epi == L.EPI_GELU else out
+        assert rel(T, Tref) < 2e-5
+        assert rel(_unsplit(U, S, Rp), Uref) < 3e-5
+        assert rel(y.float(), ref) < 6e-3 and _block_rel(y, ref) < 8e-3
+        if epi == L.EPI_GELU:
+            assert rel(out[1].float(), torch.nn.functional.gelu(y.float())) < 6e-3
+    del ref
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("M,N,K0,R,S,epi", [
+    (1000, 768, 768, 16, 1, 0), (777, 768, 2304, 8, 3, 0), (640, 1024, 4096, 32, 4, 0), (515, 3072, 768, 16, 1, 2),
+    (50432, 768, 2304, 16, 3, 0), (50432, 768, 3072, 16, 4, 0), (50432, 3072, 768, 16, 1, 2)])   # qkv / fc1 / fc2 dX
+def test_gemm_side_tiles_backward(K, M, N, K0, R, S, epi):
+    """The dX GEMM with its side tiles (G = dY [M, K0] against W^T stored [N, K0]): dU_s = G_s B per K-slice,
+    dThat = sum_s cs_s (.) dU_s feeds the adapter-transpose segment, dcs_s = sum_m dU_s (.) T is accumulated."""
+    from cara_b200 import _lib as L
+    Rp = K.round_rank(R)
+    g = torch.Generator(device="cuda").manual_seed(22)
+    G = (torch.randn(M, K0, device="cuda", generator=g) * 0.5).to(BF16)
+    Wt = (torch.randn(N, K0, device="cuda", generator=g) * 0.05).to(BF16)
+    wk = K0 // S
+    Bf = torch.randn(wk, R, device="cuda", generator=g) * 0.1          # out-side factor (per K-slice of G)
+    A = torch.randn(N, R, device="cuda", generator=g) * 0.2            # in-side factor: dX += dThat A^T
+    cs = torch.zeros(S, Rp, device="cuda"); cs[:, :R] = torch.randn(S, R, device="cuda", generator=g)
+    T = torch.randn(M, Rp, device="cuda", generator=g)
+    _, b_t2 = K.factor_operands(Bf, Rp)
+    a_ext, _ = K.factor_operands(A, Rp)
+    aux = torch.randn(M, N, device="cuda", generator=g).to(BF16) if epi == L.EPI_DGELU else None
+    dU = [torch.nn.functional.pad(G[:, s * wk:(s + 1) * wk].double() @ Bf.double(), (0, Rp - R)).float() for s in range(S)]
+    dTref = sum(dU[s] * cs[s] for s in range(S))
+    ref = G.float() @ Wt.float().T + dTref[:, :R] @ A.T
+    if aux is not None:
+        u = aux.float().requires_grad_(True)
+        torch.nn.functional.gelu(u).sum().backward()
+        ref = ref * u.grad
+    dcs_ref = torch.stack([(dU[s] * T).sum(0) for s in range(S)])
+    dcs = torch.zeros(S, Rp, device="cuda")
+    for rep_ in range(2):
+        dT = torch.full((M, 3 * Rp), float("nan"), device="cuda", dtype=BF16)
+        side = K.Side(L.SIDE_BWD, b_t2, cs, T, dT, dcs)
+        dx = K.gemm_cp(G, Wt, a1=dT, b1=a_ext, ext_slices=1, epi=epi, aux=aux, side=side)
+        assert rel(_unsplit(dT, 1, Rp), dTref) < 3e-5
+        assert rel(dx.float(), ref) < 6e-3 and _block_rel(dx, ref) < 8e-3
+        assert rel(dcs, (rep_ + 1) * dcs_ref) < 1e-4               # accumulated, not overwritten
+    del ref
+    torch.cuda.empty_cache()
+
+
 def test_gemm_adapter_segment_split_precision(K):
     """End to end through the split operands: x A diag(c) B^T added by the GEMM's adapter segment is accurate
     to ~1e-4 relative (a single-bf16 chain would sit at ~3e-3)."""

@@ -28,7 +28,7 @@ def check(rc, what):
     e = torch.cuda.Event(enable_timing=True); e.record()
     trace.append((what + tag[0], pending[0], e)); tag[0] = ""
 def gemm(a0, b0, *args, **kw):
-    tag[0] = " M%d N%d K%d epi%d%s" % (a0.shape[0], b0.shape[0], a0.shape[1], kw.get("epi", 0), " +ext" if kw.get("a1") is not None else "")
+    tag[0] = " M%d N%d K%d epi%d%s" % (a0.shape[0], b0.shape[0], a0.shape[1], kw.get("epi", 0), (" +ext" if kw.get("a1") is not None else "") + (" +side" if kw.get("side") is not None else ""))
     return orig_gemm(a0, b0, *args, **kw)
 K._prep, L.check, K.gemm_cp = prep, check, gemm
 steps = 3
