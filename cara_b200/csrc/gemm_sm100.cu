@@ -504,13 +504,12 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         uint32_t w0[32];                                          // first (or only) output of this step, packed bf16
         if (EPI == EPI_DGELU) {
-          // dX through GELU: multiply by gelu'(u), u = saved fc1 pre-activation
+          // dX through GELU: multiply by gelu'(u), which fc1's forward epilogue saved (aux)
           const uint32_t* uw = reinterpret_cast<const uint32_t*>(ux);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 f = unpack_bf16(uw[j]);
-            w0[j] = (p.debug & 8) ? pack_bf16(__uint_as_float(r[2 * j]) * f.x, __uint_as_float(r[2 * j + 1]) * f.y)
-                                  : pack_bf16(__uint_as_float(r[2 * j]) * gelu_grad_fast(f.x), __uint_as_float(r[2 * j + 1]) * gelu_grad_fast(f.y));
+            w0[j] = pack_bf16(__uint_as_float(r[2 * j]) * f.x, __uint_as_float(r[2 * j + 1]) * f.y);
           }
           if (ci + 1 < NCH) {                                     // next step's operand: in flight during the staging below
             const uint4* src = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow < p.M ? grow : 0) * p.ldaux +
@@ -527,6 +526,27 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (EBUFS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
         }
         __syncwarp();
+        uint32_t w1[EPI == EPI_GELU ? 32 : 1];                    // fc1: GELU(u) (second output)
+        if constexpr (EPI == EPI_GELU) {
+          // fc1: `out` (training only) keeps gelu'(u) for backward, `out2` gets GELU(u) for fc2; both are evaluated
+          // on the bf16-rounded pre-activation u.
+          if (p.out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 f = unpack_bf16(w0[j]);
+              float2 g, gp;
+              gelu_pair_h2(f.x, f.y, g, gp);
+              w0[j] = pack_bf16(gp.x, gp.y);
+              w1[j] = pack_bf16(g.x, g.y);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 f = unpack_bf16(w0[j]);
+              w1[j] = pack_bf16(gelu_fast(f.x), gelu_fast(f.y));
+            }
+          }
+        }
         if ((EPI != EPI_GELU || p.out != nullptr) && !(p.debug & 4)) {
           stage_row(buf, w0);
           fence_proxy_async();                                    // staging writes -> visible to the TMA engine
@@ -536,16 +556,8 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tma_store_commit();
           }
         }
-        if (EPI == EPI_GELU) {
-          // fc1: `out` keeps the pre-activation for backward, `out2` gets GELU(u) for fc2.  GELU is applied to the
-          // bf16-rounded pre-activation so forward and backward see the same u.  The math runs while the TMA engine
-          // is still reading the pre-activation out of the (single) staging buffer.
-          uint32_t w1[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 f = unpack_bf16(w0[j]);
-            w1[j] = (p.debug & 8) ? pack_bf16(f.x + 1.0f, f.y + 1.0f) : pack_bf16(gelu_fast(f.x), gelu_fast(f.y));
-          }
+        if constexpr (EPI == EPI_GELU) {
+          // second output through the same (single) staging buffer
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           stage_row(buf, w1);

@@ -1,5 +1,6 @@
 // Scalar math shared by the kernels: exact-erf GELU (timm's nn.GELU, cara.py:84) and its derivative.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace cara {
@@ -53,6 +54,37 @@ __device__ __forceinline__ float gelu_grad_fast(float u) {
   gelu_terms(a, w, e);
   const float r = e * fmaf(a, 0.3989422804014327f, -0.5f * w);
   return u < 0.0f ? -r : 1.0f + r;
+}
+// Both GELU(u) and GELU'(u) for TWO elements at once in packed half arithmetic (fc1's training epilogue keeps the
+// derivative for backward instead of the pre-activation, so the fc2 dX epilogue is a plain multiply):
+//   p = Phi(-|u|) = 2^q(|u|)  (the same degree-6 fit as gelu_fast),   GELU(u)  = max(u, 0) - |u| p
+//   Phi(u) = p + [u >= 0] (1 - 2p),   phi(u) = 2^(-u^2 log2(e)/2 - log2 sqrt(2 pi)),   GELU'(u) = Phi(u) + u phi(u)
+// 4 MUFU.EX2.F16 + ~16 packed ops per PAIR.  Inputs are bf16 values (exact in half); half's 11-bit mantissa
+// puts the error of p at <= 0.5 % where p matters, i.e. <= 1e-3 absolute on either output -- below the 2^-9 relative
+// rounding of the bf16 outputs they are stored as (checked against the exact-erf forms in tests/test_kernels_gpu.py).
+__device__ __forceinline__ __half2 ex2_h2(__half2 x) {       // MUFU.EX2.F16 per half (h2exp2 goes through fp32 and back)
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ void gelu_pair_h2(float ux, float uy, float2& g, float2& gp) {
+  const __half2 u = __floats2half2_rn(ux, uy);
+  const __half2 a = __hmin2(__habs2(u), __float2half2_rn(6.0f));
+  __half2 q = __hfma2(a, __float2half2_rn(3.042068784e-05f), __float2half2_rn(-7.316191914e-04f));
+  q = __hfma2(a, q, __float2half2_rn(7.908979431e-03f));
+  q = __hfma2(a, q, __float2half2_rn(-5.307019129e-02f));
+  q = __hfma2(a, q, __float2half2_rn(-4.590840042e-01f));
+  q = __hfma2(a, q, __float2half2_rn(-1.151080370e+00f));
+  q = __hfma2(a, q, __float2half2_rn(-1.000007629e+00f));
+  const __half2 p = ex2_h2(q);
+  const __half2 zero = __float2half2_rn(0.0f);
+  const __half2 gh = __hfma2(__hneg2(a), p, __hmax2(u, zero));
+  const __half2 ge = __hge2(u, zero);                                   // 1.0 where u >= 0
+  const __half2 Phi = __hfma2(ge, __hfma2(__float2half2_rn(-2.0f), p, __float2half2_rn(1.0f)), p);
+  const __half2 e = ex2_h2(__hfma2(__hmul2(u, u), __float2half2_rn(-0.72134752f), __float2half2_rn(-1.32574806f)));
+  const __half2 gph = __hfma2(u, e, Phi);
+  g = __half22float2(gh);
+  gp = __half22float2(gph);
 }
 __device__ __forceinline__ float gelu_exact(float u) {
   return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f));

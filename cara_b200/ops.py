@@ -190,7 +190,8 @@ class CPLinearFunction(torch.autograd.Function):
 
 class CPMlpFunction(torch.autograd.Function):
     """cp_mlp (cara.py:72-95): fc1 + adapter -> exact-erf GELU -> fc2 + adapter, as one unit so the
-    GELU is applied in the fc1 GEMM epilogue and its derivative in the fc2 dX GEMM epilogue."""
+    GELU and its derivative are both evaluated in the fc1 GEMM epilogue (the derivative is what is kept for backward:
+    the fc2 dX GEMM epilogue only multiplies by it)."""
 
     @staticmethod
     def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, fz1, ops1, fz2, ops2, sink1=None, sink2=None):
@@ -201,20 +202,21 @@ class CPMlpFunction(torch.autograd.Function):
             if train:
                 sink1[0].pending[sink1[1]] += 1
                 sink2[0].pending[sink2[1]] += 1
-        (u, g), T1, U1 = _cp_linear_fwd(x, fz1, bias1 if bias1 is not None else fz1.bias, ops1, epi=L.EPI_GELU,
-                                        want_pre=train, train=train)
+        # gp = gelu'(u), g = GELU(u) from the fc1 epilogue (u = fc1 pre-activation, never stored)
+        (gp, g), T1, U1 = _cp_linear_fwd(x, fz1, bias1 if bias1 is not None else fz1.bias, ops1, epi=L.EPI_GELU,
+                                         want_pre=train, train=train)
         y, T2, U2 = _cp_linear_fwd(g, fz2, bias2 if bias2 is not None else fz2.bias, ops2, train=train)
         ctx.fz1, ctx.ops1, ctx.fz2, ctx.ops2 = fz1, ops1, fz2, ops2
         ctx.sink1, ctx.sink2 = sink1, sink2
-        ctx.save_for_backward(x, u, g, T1, U1, T2, U2)
+        ctx.save_for_backward(x, gp, g, T1, U1, T2, U2)
         return y
 
     @staticmethod
     def backward(ctx, G):
-        x, u, g, T1, U1, T2, U2 = ctx.saved_tensors
+        x, gp, g, T1, U1, T2, U2 = ctx.saved_tensors
         ni = ctx.needs_input_grad
         du, dA2, dcs2, dB2, db2 = _cp_linear_bwd(G.contiguous(), g, ctx.fz2, ctx.ops2, T2, U2, True, ni[8],
-                                                 dgelu_aux=u, sink=ctx.sink2)
+                                                 dgelu_aux=gp, sink=ctx.sink2)
         dx, dA1, dcs1, dB1, db1 = _cp_linear_bwd(du, x, ctx.fz1, ctx.ops1, T1, U1, ni[0], ni[4], sink=ctx.sink1)
         return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None, None, None
 

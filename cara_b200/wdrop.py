@@ -112,18 +112,18 @@ class DropMlpFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, mod, t1, t2, p):
-        (u, g), ctx.s1 = _fwd(x, mod.fc1, t1, p, epi=L.EPI_GELU)
+        (gp, g), ctx.s1 = _fwd(x, mod.fc1, t1, p, epi=L.EPI_GELU)   # gp = gelu'(u), g = GELU(u)
         y, ctx.s2 = _fwd(g, mod.fc2, t2, p)
-        ctx.save_for_backward(x, u, g)
+        ctx.save_for_backward(x, gp, g)
         return y
 
     @staticmethod
     def backward(ctx, G):
-        x, u, g = ctx.saved_tensors
+        x, gp, g = ctx.saved_tensors
         G = G.contiguous()
         ni = ctx.needs_input_grad
         s1, s2 = ctx.s1, ctx.s2
-        du = K.gemm_cp(G, s2.wt, epi=L.EPI_DGELU, aux=u)
+        du = K.gemm_cp(G, s2.wt, epi=L.EPI_DGELU, aux=gp)
         dA2, dcs2, dB2, db2 = _factor_grads(G, g, s2.mask, s2.A, s2.Q, s2.t, ni[8])
         dx = K.gemm_cp(du, s1.wt) if ni[0] else None
         dA1, dcs1, dB1, db1 = _factor_grads(du, x, s1.mask, s1.A, s1.Q, s1.t, ni[4])

@@ -35,8 +35,9 @@ CARA_API int cara_set_device(int device);
  *   out[M,N] = A0[M,K0] * B0[N,K0]^T + bias[N]
  *            + A1[M, slice*K1 : (slice+1)*K1] * B1[N mod (N/ext_slices), K1]^T     (if A1 != NULL)
  * bf16 operands, fp32 accumulation in tensor memory, bf16 outputs.
- *   epi = CARA_EPI_GELU : out (may be NULL) = pre-activation, out2 = GELU(pre-activation)
- *   epi = CARA_EPI_DGELU: out = (.) * gelu'(aux[M,N])   (dX through the fc1 activation)
+ *   epi = CARA_EPI_GELU : with u = the bf16-rounded pre-activation: out2 = GELU(u) (exact-erf form, cara.py:84);
+ *                         out (NULL for inference) = gelu'(u), kept for backward instead of u
+ *   epi = CARA_EPI_DGELU: out = (.) * aux[M,N]          (dX through the fc1 activation: aux = the saved gelu'(u))
  * Requirements: K0 % 8 == 0, N % 64 == 0, K1 % 16 == 0, 16-byte aligned bases and row pitches.
  *
  * Side tiles (side != 0): the low-rank operand A1 is itself a contraction of the SAME A0 rows with a [K0, R] factor

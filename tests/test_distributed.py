@@ -53,20 +53,31 @@ def test_gloo_world2_flat_gradient_allreduce_equals_full_batch(tmp_path):
         T.shard_batch(9, 0, 2)
 
 
-def _torchrun(nproc, extra_env):
+def _torchrun(nproc, extra_env, log_path, limit=420):
+    """torchrun of tests/_dist_workers.py; output goes to a FILE (no pipes that a lingering grandchild could keep open)
+    and the whole process group is killed when the time limit passes."""
+    import signal
     env = dict(os.environ)
     env.update(extra_env)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+    cmd = [sys.executable, "-u", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "_dist_workers.py")]
-    return subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    with open(log_path, "w") as log:
+        proc = subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=log, stderr=subprocess.STDOUT, start_new_session=True)
+        try:
+            rc = proc.wait(timeout=limit)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+            proc.wait()
+            rc = -9
+    return rc, open(log_path).read()
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("captured", ["1", "0"])
-def test_two_gpu_half_batches_equal_one_gpu_full_batch(captured):
+def test_two_gpu_half_batches_equal_one_gpu_full_batch(captured, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    r = _torchrun(2, {"CARA_GRAPH_COLLECTIVE": captured})
-    print(r.stdout[-2000:], r.stderr[-2000:])
-    assert r.returncode == 0 and "DIST_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+    rc, out = _torchrun(2, {"CARA_GRAPH_COLLECTIVE": captured}, os.path.join(str(tmp_path), "dist.log"))
+    print(out[-3000:])
+    assert rc == 0 and "DIST_OK" in out, out[-3000:]
