@@ -330,6 +330,9 @@ def run_cuda(args):
             out["cpu_baseline"] = cpu_reference(args, steps=3, warmup=1)
         print(json.dumps(out), flush=True)
     if world > 1:
+        if hasattr(step, "release"):
+            step.release()                       # captured collectives must be gone before the communicator is
+        dist.barrier()
         dist.destroy_process_group()
 
 

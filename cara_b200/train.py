@@ -170,7 +170,8 @@ class GraphedStep:
     sequence is captured once and replayed -- the host's only per-step work is the copy of the inputs into the
     graph's static buffers and one ``cudaGraphLaunch``.  With micro-batch accumulation (``accumulate`` = k > 1) the
     forward/backward graph is replayed k times and a second small graph holds the all-reduce + AdamW.
-    ``CARA_GRAPH_COLLECTIVE=0`` keeps the all-reduce and the optimizer outside the graph (eager launches).
+    On several GPUs the all-reduce and the optimizer stay outside the graph (two eager launches) unless
+    ``CARA_GRAPH_COLLECTIVE=1``.
     """
 
     def __init__(self, model, opt, x, y, world_size=1, warmup=3, accumulate=1, capture_update=None):
@@ -180,7 +181,11 @@ class GraphedStep:
         import os
         self.model, self.opt, self.world_size, self.accumulate = model, opt, world_size, int(accumulate)
         if capture_update is None:
-            capture_update = os.environ.get("CARA_GRAPH_COLLECTIVE", "1") != "0"
+            # one GPU: AdamW rides in the graph.  Several GPUs: the NCCL all-reduce (and AdamW after it) stay eager
+            # launches unless CARA_GRAPH_COLLECTIVE=1 -- a process group cannot be destroyed while a captured graph
+            # still holds its collectives (the caller must drop the GraphedStep first; see release()).
+            env = os.environ.get("CARA_GRAPH_COLLECTIVE")
+            capture_update = (world_size == 1) if env is None else env != "0"
         self.capture_update = bool(capture_update)
         self.gscale = 1.0 / (self.world_size * self.accumulate)
         self.x = torch.empty_like(x)
@@ -211,6 +216,15 @@ class GraphedStep:
             with torch.cuda.graph(self.update_graph):
                 self._update()
             self.launches_per_update = K.launch_count - before
+
+    def release(self):
+        """Drop the captured graphs (needed before ``torch.distributed.destroy_process_group()`` when the all-reduce
+        was captured: NCCL waits for every graph that references the communicator)."""
+        self.graph = None
+        self.update_graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
 
     def _fwd_bwd(self):
         if self.accumulate == 1:

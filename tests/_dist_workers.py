@@ -138,6 +138,8 @@ def _gpu_main():
               % (world, per, depth, step.capture_update, e_g, e_g_later, e_p, e_l, same, steps_dev,
                  "DIST_OK" if ok else "DIST_FAIL"), flush=True)
     sys.stdout.flush()
+    step.release()                                       # the graph holds the captured all-reduce
+    dist.barrier()
     dist.destroy_process_group()
     os._exit(0 if ok else 1)
 

@@ -74,7 +74,7 @@ def _torchrun(nproc, extra_env, log_path, limit=420):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("captured", ["1", "0"])
+@pytest.mark.parametrize("captured", ["0", "1"])
 def test_two_gpu_half_batches_equal_one_gpu_full_batch(captured, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
