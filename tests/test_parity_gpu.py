@@ -500,3 +500,30 @@ def test_lr_schedule_reaches_the_device_inside_the_graphed_step():
             want, m, v = O.adamw_update(before, gr, m, v, i + 1, lr=lr)
             assert rel(opt.flat.flat.detach().cpu(), want) < 1e-6, (i, lr)
             assert float(opt.state[1]) == i + 1 and float(opt.state[0]) == pytest.approx(lr)
+
+
+def test_vit_cp_cli_trains_saves_and_evaluates(tmp_path):
+    """the entry point end to end, as the reference's README runs it (PYTHONPATH=. python
+    image_classification/vit_cp.py --dataset= --dim=): one epoch of fine-tuning on VTAB-shaped synthetic data with the
+    reference's train-mode semantics (weight dropout 'exact', DropPath 0.1, CUDA-graph step, per-step lr of the
+    reference loop), the final test(), the checkpoint it writes, and ``--evaluate`` of that checkpoint (merged)."""
+    import glob
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    base = [sys.executable, os.path.join(root, "image_classification", "vit_cp.py"), "--dataset=cifar", "--dim=8", "--synthetic"]
+    r = subprocess.run(base + ["--epochs=1", "--batch-size=50"], cwd=str(tmp_path), env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "e: 0, l:" in r.stdout and "Accuracy:" in r.stdout, r.stdout[-2000:]
+    loss = float(r.stdout.split("e: 0, l:")[1].split(",")[0])
+    assert 3.0 < loss < 7.0, loss                                # ~ln(100) on random labels: the step ran and is finite
+    ckpts = glob.glob(os.path.join(str(tmp_path), "vit_cifar_*_seed_*.pt"))
+    assert len(ckpts) == 1, (ckpts, r.stdout[-2000:])
+    acc_train_run = float(r.stdout.strip().splitlines()[-1].split("Accuracy:")[1])
+    e = subprocess.run(base + ["--evaluate=" + ckpts[0]], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert e.returncode == 0 and "Only evaluation" in e.stdout, e.stderr[-3000:]
+    acc_eval = float(e.stdout.strip().splitlines()[-1].split("Accuracy:")[1])
+    # the merged --evaluate forward reproduces the accuracy the training run measured through the adapter kernels
+    assert abs(acc_eval - acc_train_run) <= 2.0 / 512 + 1e-9, (acc_eval, acc_train_run)
