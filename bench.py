@@ -6,7 +6,10 @@
 
 One "step" = one fine-tune iteration (reference vit_cp.py:45-50: forward, CE, backward, AdamW over CP*+head) on
 a synthetic batch of 256 images per GPU (weak scaling; frozen backbone replicated, one NCCL all-reduce of the flat
-CP+head gradient per step).  Prints ONE JSON line (rank 0).
+CP+head gradient per step).  Prints ONE JSON line (rank 0).  --config selects the other BASELINE.json configurations
+(vitl16_r32 / vith14_r32 / vitb16_eval); --global-batch G fixes the GLOBAL batch instead (strong scaling, configs[2]).
+The CPU arm (--impl reference, and cpu_baseline in the default line) is BASELINE configs[0] exactly as BASELINE.md
+section 5 specifies it: ViT-B/16 rank 8 fp32 batch 32, 1 warm-up + best of 3, oracle port, all host threads.
 """
 import argparse
 import json
