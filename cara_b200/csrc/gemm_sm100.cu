@@ -343,6 +343,21 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           continue;
         }
         const int n0 = ti.n0;
+        if (p.prefetch) {
+          // (experiment, CARA_GEMM_PREFETCH=1, off: K = 768 shapes +3 %, K >= 2304 shapes -10 %: the extra L2 requests cost
+          // more than the latency they hide)
+          // L2 prefetch of the A0 panel of this CTA's NEXT output tile.  A panel is read first by whichever of its
+          // tiles_n tiles gets there first -- a miss to HBM that all of them then wait for, and four ring slots do not
+          // cover HBM latency.  The tiles_n CTAs that will work on that panel one round from now each pull a disjoint
+          // 1/tiles_n of its k-blocks into L2 now (k-block index congruent to their column-tile index), so by then the
+          // slot loads hit L2.
+          const int t2 = t + nunits;
+          if (t2 < num_tiles) {
+            const TileInfo nx = decode_tile(t2, p.tiles_m, p.tiles_n, side_tiles != 0, p.side_la);
+            if (nx.kind == TILE_MAIN)
+              for (int kb = nx.n0 / BN; kb < p.kblocks_main; kb += p.tiles_n) tma_prefetch_2d(&mapA0, kb * BK, nx.panel * BM);
+          }
+        }
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);       // stage free
           const uint32_t sa = tiles + s * STAGE_BYTES;
@@ -697,6 +712,11 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("CARA_GEMM_DEBUG"); dbg = e != nullptr ? atoi(e) : 0; }
     args.debug = dbg;
+  }
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("CARA_GEMM_PREFETCH"); pf = e != nullptr ? atoi(e) : 0; }
+    args.prefetch = pf;
   }
   args.tiles_m = (d.M + BM - 1) / BM;
   args.tiles_n = side_only ? 0 : (d.N + BN - 1) / BN;

@@ -24,6 +24,7 @@ struct GemmArgs {
   __nv_bfloat16* out; int ldo;
   __nv_bfloat16* out2; int ldo2;
   const __nv_bfloat16* aux; int ldaux;
+  int prefetch;       // 1: L2-prefetch the A0 panel of the CTA's next tile (experiment CARA_GEMM_PREFETCH=1, default 0)
   int debug;          // experiments (CARA_GEMM_DEBUG): 1 = epilogue only drains TMEM, 4 = no output staging, 16 = no side-tile flag wait
   // rank-R side tiles (one per 128-row panel, ahead of the panel's output tiles; see gemm_sm100.cu)
   int side;             // GemmSide
