@@ -58,7 +58,9 @@ constexpr int EBUF = 32 * EC * 2;               // 4 KB staging buffer: 32 rows 
 constexpr int SIDE_RED = 4 * 32;                // dcs partial sums of this CTA (slices x rank)
 __host__ __device__ constexpr int num_epi_warps(int epi) { return epi == EPI_NONE ? 4 : 8; }
 __host__ __device__ constexpr int epi_bufs(int epi) { return epi == EPI_NONE ? 2 : 1; }   // staging buffers per warp
-__host__ __device__ constexpr int num_threads(int epi) { return 64 + 32 * num_epi_warps(epi); }
+// SW: four extra warps that drain the side tiles (plain epilogue kind only: the 8-warp GELU kinds are at the register
+// ceiling of 384 threads and keep the stand-alone rows pass)
+__host__ __device__ constexpr int num_threads(int epi, bool sw = false) { return 64 + 32 * num_epi_warps(epi) + (sw ? 128 : 0); }
 __host__ __device__ constexpr int gemm_smem(int epi) {
   return STAGES * STAGE_BYTES + num_epi_warps(epi) * epi_bufs(epi) * EBUF + 1024 /*align slack*/ + 512 /*barriers*/ +
          SIDE_RED * 4;
@@ -94,11 +96,13 @@ __device__ __forceinline__ void wait_panel(const unsigned* flags, unsigned gen) 
   }
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
-// The two TMEM accumulator buffers: every tile (output or side) takes buffer `cur` and flips it; uses[b] counts the
-// uses of buffer b so far and gives the mbarrier phase parities.  (Tried: letting a side tile BORROW the next output
-// tile's buffer and draining it between two steps of the running epilogue, so that the MMA warp never waits for a full
-// epilogue behind a side tile -- the polling state pushed the 168-register GELU' epilogue into spills and every kind
-// got slower; profiles/r02_side_tiles.md.)
+// The two TMEM accumulator buffers.  An OUTPUT tile takes buffer `cur` and flips it; uses of a buffer are counted and give
+// the mbarrier phase parities.  A SIDE tile takes no turn in that rotation: it borrows `cur` -- the buffer the next
+// output tile of this CTA will use, already drained -- for its few columns, four dedicated warps drain it the moment
+// its MMAs retire (sfull / sempty barriers), and the MMA warp then starts the next output tile in the same buffer
+// while the output-tile epilogue warps are still busy with the previous tile in the other one.  (Round-2 history: with
+// a turn in the rotation every side tile cost a whole un-overlapped epilogue; draining it from the output-tile
+// epilogue warps between their steps pushed the 168-register GELU' epilogue into spills -- profiles/r02_side_tiles.md.)
 struct AccState {
   int cur;
   uint32_t u0, u1;
@@ -246,8 +250,8 @@ __device__ __noinline__ void side_epilogue(const GemmArgs& p, uint32_t t_row, in
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(num_threads(EPI), 1)
+template <int EPI, bool SW>
+__global__ void __launch_bounds__(num_threads(EPI, SW), 1)
 gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAux,
@@ -267,7 +271,8 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  const uint32_t sfull_bar = bars + 8u * (2 * STAGES + 4), sempty_bar = bars + 8u * (2 * STAGES + 5);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   volatile uint32_t* gen_slot_ptr = tmem_slot_ptr + 1;
   float* side_red = reinterpret_cast<float*>(smem_raw + (bars + 512u - raw));
@@ -298,6 +303,8 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EW);               // one arrive per epilogue warp
     }
+    mbar_init(sfull_bar, 1);
+    mbar_init(sempty_bar, 4);                     // one arrive per side-drain warp
     if (p.tiles_n > 0) tma_prefetch_desc(&mapOut);
     if (EPI != EPI_NONE) tma_prefetch_desc(&mapAux);
     fence_mbar_init();
@@ -385,12 +392,18 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       AccState acc{0, 0u, 0u};
+      uint32_t side_count = 0;                    // side tiles issued so far by this CTA
+      bool side_undrained = false;                // the last side tile's columns may still be unread
       for (int t = unit; t < num_tiles; t += nunits) {
         const TileInfo ti = decode_tile(t, p.tiles_m, p.tiles_n, side_tiles != 0, p.side_la);
         if (ti.kind == TILE_SKIP) continue;
         const bool is_side = ti.kind == TILE_SIDE;
         const int as = acc.cur;
-        mbar_wait(tempty_bar(as), acc.parity(as) ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait(tempty_bar(as), acc.parity(as) ^ 1u);   // the output-tile epilogue has drained this accumulator
+        if (side_undrained) {                     // ... and the side warps the columns the last side tile borrowed
+          mbar_wait(sempty_bar, (side_count - 1u) & 1u);
+          side_undrained = false;
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
         const int nkb = is_side ? side_fills : kblocks;
@@ -426,11 +439,37 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           // when these MMAs retire: free the smem stage / publish the accumulator
           umma_commit(empty_bar(s));
-          if (kb == nkb - 1) umma_commit(tfull_bar(as));
+          if (kb == nkb - 1) umma_commit(is_side ? sfull_bar : tfull_bar(as));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        acc.advance();
+        if (is_side) {
+          ++side_count;
+          side_undrained = true;
+        } else {
+          acc.advance();
+        }
       }
+    }
+  } else if (SW && warp >= 2 + EW) {
+    // ------------------------------------------------------------------ side-drain warps (one per TMEM lane group)
+    const int lg = warp & 3;
+    int cur = 0;                                  // mirrors AccState::cur of the MMA warp: flips on every output tile
+    uint32_t k = 0;                               // side tiles seen so far
+    for (int t = unit; t < num_tiles; t += nunits) {
+      const TileInfo ti = decode_tile(t, p.tiles_m, p.tiles_n, side_tiles != 0, p.side_la);
+      if (ti.kind == TILE_SKIP) continue;
+      if (ti.kind == TILE_MAIN) { cur ^= 1; continue; }
+      mbar_wait(sfull_bar, k & 1u);
+      ++k;
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(cur * BN);
+      const int grow_s = ti.panel * BM + lg * 32 + lane;
+      if (p.side_rp == 16) side_epilogue<16>(p, t_row, grow_s, lane, side_red, sempty_bar);
+      else side_epilogue<32>(p, t_row, grow_s, lane, side_red, sempty_bar);
+      // publish this warp's 32 rows: the warp-level barrier orders the lanes' stores before lane 0's release,
+      // which is cumulative (PTX memory model) -- only that one thread waits for the stores to become visible
+      __syncwarp();
+      if (lane == 0) st_release_u32(p.sync + 2 + 4 * ti.panel + lg, gen);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -449,34 +488,10 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4)),
                      "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
     };
-    // side tile of `panel` in accumulator buffer `b` (its tfull phase has completed): drain, emit, publish
-    auto service_side = [&](int panel_s, int b) {
-      tc_fence_after();
-      if (ew < 4) {
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(b * BN);
-        const int grow_s = panel_s * BM + lg * 32 + lane;
-        if (p.side_rp == 16) side_epilogue<16>(p, t_row, grow_s, lane, side_red, tempty_bar(b));
-        else side_epilogue<32>(p, t_row, grow_s, lane, side_red, tempty_bar(b));
-        // publish this warp's 32 rows: the warp-level barrier orders the lanes' stores before lane 0's release,
-        // which is cumulative (PTX memory model) -- only that one thread waits for the stores to become visible
-        __syncwarp();
-        if (lane == 0) st_release_u32(p.sync + 2 + 4 * panel_s + lg, gen);
-      } else {                                    // (8-warp kinds: the upper-column warps have nothing to read)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(b));
-      }
-    };
     for (int t = unit; t < num_tiles; t += nunits) {
       const TileInfo ti = decode_tile(t, p.tiles_m, p.tiles_n, side_tiles != 0, p.side_la);
-      if (ti.kind == TILE_SKIP) continue;
+      if (ti.kind != TILE_MAIN) continue;         // (side tiles belong to the side-drain warps)
       const int as = acc.cur;
-      if (ti.kind == TILE_SIDE) {
-        mbar_wait(tfull_bar(as), acc.parity(as));
-        service_side(ti.panel, as);
-        acc.advance();
-        continue;
-      }
       const int panel = ti.panel;
       const int m0 = panel * BM;
       const int grow = m0 + lg * 32 + lane;       // global row of this thread
@@ -649,18 +664,18 @@ struct Maps {
   CUtensorMap a0, b0, a1, b1, out, aux, p;
 };
 
-template <int EPI>
+template <int EPI, bool SW>
 static cudaError_t launch_epi(const Maps& m, const GemmArgs& args, int grid, cudaStream_t st) {
   static bool attr_done = false;
   constexpr int smem = gemm_smem(EPI);
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_cp_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_cp_kernel<EPI, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(num_threads(EPI));
+  cfg.blockDim = dim3(num_threads(EPI, SW));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -669,7 +684,7 @@ static cudaError_t launch_epi(const Maps& m, const GemmArgs& args, int grid, cud
   cfg.attrs = attr;
   // side tiles synchronise CTAs of ONE launch through global flags: never overlap such a launch with its neighbours
   cfg.numAttrs = ((pdl_mask() & 1) && args.side == SIDE_NONE) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_cp_kernel<EPI>, m.a0, m.b0, m.a1, m.b1, m.out, m.aux, m.p, args);
+  return cudaLaunchKernelEx(&cfg, gemm_cp_kernel<EPI, SW>, m.a0, m.b0, m.a1, m.b1, m.out, m.aux, m.p, args);
 }
 
 static int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
@@ -725,6 +740,7 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   args.side = SIDE_NONE;
   if (d.side != SIDE_NONE) {
     if (d.side != SIDE_FWD && d.side != SIDE_BWD) return -17;
+    if (!side_only && d.epi != EPI_NONE) return -20;              // side-drain warps exist for the plain epilogue kind only
     if ((d.side_rp != 16 && d.side_rp != 32) || d.side_slices < 1 || d.side_slices > 4) return -17;
     if (d.P == nullptr || d.side_scales == nullptr || d.side_U == nullptr || d.sync == nullptr) return -17;
     if (d.side == SIDE_BWD && d.side_T == nullptr) return -17;
@@ -794,9 +810,11 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   }
   cudaError_t e;
   switch (side_only ? EPI_NONE : d.epi) {
-    case EPI_NONE: e = launch_epi<EPI_NONE>(m, args, grid, st); break;
-    case EPI_GELU: e = launch_epi<EPI_GELU>(m, args, grid, st); break;
-    default: e = launch_epi<EPI_DGELU>(m, args, grid, st); break;
+    case EPI_NONE:
+      e = args.side != SIDE_NONE ? launch_epi<EPI_NONE, true>(m, args, grid, st) : launch_epi<EPI_NONE, false>(m, args, grid, st);
+      break;
+    case EPI_GELU: e = launch_epi<EPI_GELU, false>(m, args, grid, st); break;
+    default: e = launch_epi<EPI_DGELU, false>(m, args, grid, st); break;
   }
   return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);
 }

@@ -105,7 +105,7 @@ def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True, train=Tr
     contraction T = x A, Uhat_s = cs_s (.) T that feeds the segment runs as its own pass (default) or, with
     CARA_SIDE_TILES=1, as side tiles of the same GEMM launch."""
     T = U = None
-    if ops is not None and not K.side_tiles:
+    if ops is not None and not (K.side_tiles and epi == L.EPI_NONE):
         # default: the row contraction T = x A, Uhat_s = cs_s (.) T as its own HBM-bound pass, then the GEMM
         T, U = K.adapter_rows_fwd(x, ops.a_t2, ops.cs_pad)
         y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_ext, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
@@ -140,7 +140,7 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink
         zs = torch.split(z, sizes)
         dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
         colsum = zs[3] if need_bias else None
-    if not K.side_tiles:
+    if not (K.side_tiles and epi == L.EPI_NONE):
         # the three readers of G run back to back: for the C-wide projections G (77 MB at ViT-B) stays in the 126 MB L2
         dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
         K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
