@@ -38,6 +38,19 @@ class GemmDesc(C.Structure):
 
 _P = C.c_void_p
 
+
+class StageDesc(C.Structure):
+    """struct cara_stage_desc (include/cara_b200.h)."""
+    _PTRS_IN = ["A1", "A3", "A4", "P1", "P2", "R1", "R2", "bias1", "bias2", "bias3", "ai", "pi", "mi", "s_a", "s_m",
+                "fb_proj", "fb_fc1", "fb_fc2"]
+    _PTRS_OUT = ["kr", "cs_qkv", "cs_proj", "cs_fc1", "a_fc2", "cs_fc2", "b_proj", "b_fc1", "b_fc2",
+                 "cs_qkv_pad", "cs_proj_pad", "cs_fc1_pad", "cs_fc2_pad"]
+    _PTRS_G = ["g_kr", "g_cs_qkv", "g_cs_proj", "g_cs_fc1", "g_a_fc2", "g_cs_fc2", "g_b_proj", "g_b_fc1", "g_b_fc2"]
+    _LDS = ["ld_kr", "ld_cs_qkv", "ld_cs_proj", "ld_cs_fc1", "ld_a_fc2", "ld_cs_fc2"]
+    _PTRS_D = ["dA1", "dA3", "dA4", "dP1", "dP2", "dR1", "dR2", "dbias1", "dbias2", "dbias3"]
+    _fields_ = ([(n, C.c_int) for n in ("R", "Rp", "C", "D", "L")] + [(n, C.c_void_p) for n in _PTRS_IN + _PTRS_OUT + _PTRS_G] +
+                [(n, C.c_long) for n in _LDS] + [(n, C.c_void_p) for n in _PTRS_D])
+
 _SIGS = {
     "cara_abi_version": (C.c_int, []),
     "cara_last_error": (C.c_char_p, []),
@@ -58,6 +71,7 @@ _SIGS = {
     "cara_patchify": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cara_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "cara_factor_operands": (C.c_int, [_P, _P, _P, C.c_long, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_stage_terms": (C.c_int, [C.POINTER(StageDesc), C.c_int, _P]),
     "cara_merge_weights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cara_adamw_step": (C.c_int, [_P, _P, _P, _P, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int, C.c_float, _P]),

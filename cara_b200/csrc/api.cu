@@ -136,6 +136,25 @@ int cara_factor_operands(const float* F, void* ext, void* t2, long batch, int ro
   CARA_RET(cara::factor_operands_launch(F, static_cast<bf16*>(ext), static_cast<bf16*>(t2), batch, rows, R, Rp,
                                         CARA_STREAM(stream)), "cara_factor_operands");
 }
+int cara_stage_terms(const cara_stage_desc* d, int backward, void* stream) {
+  if (d == nullptr) return fail(-71, "cara_stage_terms: null descriptor");
+  cara::StageArgs a{};
+  a.R = d->R; a.Rp = d->Rp; a.C = d->C; a.D = d->D; a.L = d->L;
+  a.A1 = d->A1; a.A3 = d->A3; a.A4 = d->A4; a.P1 = d->P1; a.P2 = d->P2; a.R1 = d->R1; a.R2 = d->R2;
+  a.bias1 = d->bias1; a.bias2 = d->bias2; a.bias3 = d->bias3;
+  a.ai = d->ai; a.pi = d->pi; a.mi = d->mi; a.s_a = d->s_a; a.s_m = d->s_m;
+  a.fb_proj = d->fb_proj; a.fb_fc1 = d->fb_fc1; a.fb_fc2 = d->fb_fc2;
+  a.kr = d->kr; a.cs_qkv = d->cs_qkv; a.cs_proj = d->cs_proj; a.cs_fc1 = d->cs_fc1; a.a_fc2 = d->a_fc2; a.cs_fc2 = d->cs_fc2;
+  a.b_proj = d->b_proj; a.b_fc1 = d->b_fc1; a.b_fc2 = d->b_fc2;
+  a.cs_qkv_pad = d->cs_qkv_pad; a.cs_proj_pad = d->cs_proj_pad; a.cs_fc1_pad = d->cs_fc1_pad; a.cs_fc2_pad = d->cs_fc2_pad;
+  a.g_kr = d->g_kr; a.g_cs_qkv = d->g_cs_qkv; a.g_cs_proj = d->g_cs_proj; a.g_cs_fc1 = d->g_cs_fc1; a.g_a_fc2 = d->g_a_fc2;
+  a.g_cs_fc2 = d->g_cs_fc2; a.g_b_proj = d->g_b_proj; a.g_b_fc1 = d->g_b_fc1; a.g_b_fc2 = d->g_b_fc2;
+  a.ld_kr = d->ld_kr; a.ld_cs_qkv = d->ld_cs_qkv; a.ld_cs_proj = d->ld_cs_proj; a.ld_cs_fc1 = d->ld_cs_fc1;
+  a.ld_a_fc2 = d->ld_a_fc2; a.ld_cs_fc2 = d->ld_cs_fc2;
+  a.dA1 = d->dA1; a.dA3 = d->dA3; a.dA4 = d->dA4; a.dP1 = d->dP1; a.dP2 = d->dP2; a.dR1 = d->dR1; a.dR2 = d->dR2;
+  a.dbias1 = d->dbias1; a.dbias2 = d->dbias2; a.dbias3 = d->dbias3;
+  CARA_RET(cara::stage_launch(a, backward, CARA_STREAM(stream)), "cara_stage_terms");
+}
 int cara_merge_weights(const float* W, const float* A, const float* Bf, const float* cs, void* Weff, int N, int K,
                        int slices, int R, void* stream) {
   CARA_RET(cara::merge_launch(W, A, Bf, cs, static_cast<bf16*>(Weff), N, K, slices, R, CARA_STREAM(stream)), "cara_merge_weights");

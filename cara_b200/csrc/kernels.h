@@ -110,6 +110,21 @@ int sgemm_launch(const float* A, long ars, long acs, const float* B, long brs, l
                  const float* bias, int M, int N, int K, float alpha, float beta, float* ws, long ws_floats,
                  cudaStream_t st);
 
+// Per-step staging of the CP factors and its chain rule (misc.cu).  Forward fields first, then the backward's.
+struct StageArgs {
+  int R, Rp, C, D, L;
+  const float *A1, *A3, *A4, *P1, *P2, *R1, *R2, *bias1, *bias2, *bias3;     // CP_* parameters (fp32, contiguous)
+  const int *ai, *pi, *mi;                                                   // attn_idx, attn idx, mlp idx per layer
+  const float *s_a, *s_m;                                                    // adapter scale per layer
+  const float *fb_proj, *fb_fc1, *fb_fc2;                                    // frozen biases stacked over the layers
+  float *kr, *cs_qkv, *cs_proj, *cs_fc1, *a_fc2, *cs_fc2, *b_proj, *b_fc1, *b_fc2;   // forward outputs
+  float *cs_qkv_pad, *cs_proj_pad, *cs_fc1_pad, *cs_fc2_pad;                 // ... and their [.., Rp] copies (zero padded by the caller)
+  const float *g_kr, *g_cs_qkv, *g_cs_proj, *g_cs_fc1, *g_a_fc2, *g_cs_fc2, *g_b_proj, *g_b_fc1, *g_b_fc2;   // incoming gradients (null = none)
+  long ld_kr, ld_cs_qkv, ld_cs_proj, ld_cs_fc1, ld_a_fc2, ld_cs_fc2;         // their row pitches (R or Rp)
+  float *dA1, *dA3, *dA4, *dP1, *dP2, *dR1, *dR2, *dbias1, *dbias2, *dbias3; // backward outputs (zero filled by the caller)
+};
+int stage_launch(const StageArgs& a, int backward, cudaStream_t st);
+
 int factor_operands_launch(const float* F, __nv_bfloat16* ext, __nv_bfloat16* t2, long batch, int rows, int R, int Rp,
                            cudaStream_t st);
 

@@ -139,6 +139,225 @@ int factor_operands_launch(const float* F, __nv_bfloat16* ext, __nv_bfloat16* t2
   return cudaGetLastError() == cudaSuccess ? 0 : -65;
 }
 
+// ---------------------------------------------------------------- per-step staging of the CP factors
+// The twelve CP_* parameters of the root model (cara.py:112-125) -> the per-layer, per-projection terms the kernels
+// consume, and the chain rule back (SURVEY A.2 "chain to parameters").  One launch each way instead of ~90 tiny torch
+// kernels per step.  All tensors fp32; R = rank, Rp = rank padded to 16 / 32 (the padded copies of the cs terms are what
+// the kernels read; they carry no gradient).
+//   kr[h*D+d, r]        = A3[h,r] A4[d,r]                          (out-side factor of qkv: Khatri-Rao of CP_A3, CP_A4)
+//   cs_qkv[l,k,r]       = s_a[l] R1[r] A1[ai[l]+k, r]              (cara.py:26: rows attn_idx .. attn_idx+2)
+//   cs_proj[l,r]        = s_a[l] R2[r] P1[pi[l], r]                (cara.py:51)
+//   cs_fc1[l,a,r]       = s_m[l] R2[r] P1[mi[l]+a, r]              (cara.py:72)
+//   a_fc2[l, a*C+b, r]  = P1[mi[l]+4+a, r] P2[b,r]                 (cara.py:73: in-side factor of fc2)
+//   cs_fc2[l,r]         = s_m[l] R2[r]
+//   b_proj[l,c] = fb_proj[l,c] + s_a[l] bias1[c];  b_fc1[l,c] = fb_fc1[l,c] + s_m[l] bias2[c];  b_fc2 likewise with bias3
+__global__ void __launch_bounds__(256)
+stage_fwd_kernel(const StageArgs a) {
+  const int R = a.R, Rp = a.Rp, C = a.C, D = a.D, L = a.L;
+  const long n_kr = static_cast<long>(C) * R, n_q = static_cast<long>(L) * 3 * R, n_p = static_cast<long>(L) * R,
+             n_1 = static_cast<long>(L) * 4 * R, n_a = static_cast<long>(L) * 4 * C * R, n_bp = static_cast<long>(L) * C,
+             n_b1 = static_cast<long>(L) * 4 * C;
+  const long total = n_kr + n_q + n_p + n_1 + n_a + n_p + n_bp + n_b1 + n_bp;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
+    long j = i;
+    if (j < n_kr) {
+      const int r = static_cast<int>(j % R), row = static_cast<int>(j / R);
+      a.kr[j] = a.A3[(row / D) * R + r] * a.A4[(row % D) * R + r];
+      continue;
+    }
+    j -= n_kr;
+    if (j < n_q) {
+      const int r = static_cast<int>(j % R), k = static_cast<int>((j / R) % 3), l = static_cast<int>(j / (3 * R));
+      const float v = a.s_a[l] * a.R1[r] * a.A1[static_cast<long>(a.ai[l] + k) * R + r];
+      a.cs_qkv[j] = v;
+      a.cs_qkv_pad[(static_cast<long>(l) * 3 + k) * Rp + r] = v;
+      continue;
+    }
+    j -= n_q;
+    if (j < n_p) {
+      const int r = static_cast<int>(j % R), l = static_cast<int>(j / R);
+      const float v = a.s_a[l] * a.R2[r] * a.P1[static_cast<long>(a.pi[l]) * R + r];
+      a.cs_proj[j] = v;
+      a.cs_proj_pad[static_cast<long>(l) * Rp + r] = v;
+      continue;
+    }
+    j -= n_p;
+    if (j < n_1) {
+      const int r = static_cast<int>(j % R), k = static_cast<int>((j / R) % 4), l = static_cast<int>(j / (4 * R));
+      const float v = a.s_m[l] * a.R2[r] * a.P1[static_cast<long>(a.mi[l] + k) * R + r];
+      a.cs_fc1[j] = v;
+      a.cs_fc1_pad[(static_cast<long>(l) * 4 + k) * Rp + r] = v;
+      continue;
+    }
+    j -= n_1;
+    if (j < n_a) {
+      const int r = static_cast<int>(j % R);
+      const long row = j / R;                                    // l * 4C + k * C + b
+      const int bcol = static_cast<int>(row % C), k = static_cast<int>((row / C) % 4), l = static_cast<int>(row / (4L * C));
+      a.a_fc2[j] = a.P1[static_cast<long>(a.mi[l] + 4 + k) * R + r] * a.P2[static_cast<long>(bcol) * R + r];
+      continue;
+    }
+    j -= n_a;
+    if (j < n_p) {
+      const int r = static_cast<int>(j % R), l = static_cast<int>(j / R);
+      const float v = a.s_m[l] * a.R2[r];
+      a.cs_fc2[j] = v;
+      a.cs_fc2_pad[static_cast<long>(l) * Rp + r] = v;
+      continue;
+    }
+    j -= n_p;
+    if (j < n_bp) { a.b_proj[j] = a.fb_proj[j] + a.s_a[j / C] * a.bias1[j % C]; continue; }
+    j -= n_bp;
+    if (j < n_b1) { a.b_fc1[j] = a.fb_fc1[j] + a.s_m[j / (4 * C)] * a.bias2[j % (4 * C)]; continue; }
+    j -= n_b1;
+    a.b_fc2[j] = a.fb_fc2[j] + a.s_m[j / C] * a.bias3[j % C];
+  }
+}
+
+// Chain rule of the staging above: gradients of the nine staged tensors (any may be null; the R-wide ones come with a
+// row pitch, they are views into the Rp-wide gradient sink) -> gradients of CP_A1, CP_A3, CP_A4, CP_P1, CP_P2 (its
+// a_fc2 share), CP_R1, CP_R2, CP_bias1..3.  One thread per output element, serial reductions (at most C terms);
+// the indexed rows are added atomically into zero-filled outputs (rows are distinct for every model set_cara builds).
+__global__ void __launch_bounds__(256)
+stage_bwd_kernel(const StageArgs a) {
+  const int R = a.R, C = a.C, D = a.D, H = C / a.D, L = a.L;
+  const long n_q = static_cast<long>(L) * 3 * R, n_3 = static_cast<long>(H) * R, n_4 = static_cast<long>(D) * R,
+             n_p = static_cast<long>(L) * R, n_1 = static_cast<long>(L) * 4 * R, n_2 = static_cast<long>(C) * R;
+  const long total = n_q + R + n_3 + n_4 + n_p + n_1 + n_1 + n_2 + R + 6L * C;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
+    long j = i;
+    if (j < n_q) {                                               // dCP_A1[ai[l]+k] += s_a dcs_qkv[l,k] (.) R1
+      if (a.g_cs_qkv != nullptr) {
+        const int r = static_cast<int>(j % R), k = static_cast<int>((j / R) % 3), l = static_cast<int>(j / (3 * R));
+        atomicAdd(a.dA1 + static_cast<long>(a.ai[l] + k) * R + r,
+                  a.s_a[l] * a.g_cs_qkv[(static_cast<long>(l) * 3 + k) * a.ld_cs_qkv + r] * a.R1[r]);
+      }
+      continue;
+    }
+    j -= n_q;
+    if (j < R) {                                                 // dCP_R1 = sum_{l,k} s_a dcs_qkv[l,k] (.) A1[ai[l]+k]
+      if (a.g_cs_qkv != nullptr) {
+        const int r = static_cast<int>(j);
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l)
+          for (int k = 0; k < 3; ++k)
+            acc = fmaf(a.s_a[l] * a.g_cs_qkv[(static_cast<long>(l) * 3 + k) * a.ld_cs_qkv + r],
+                       a.A1[static_cast<long>(a.ai[l] + k) * R + r], acc);
+        a.dR1[r] = acc;
+      }
+      continue;
+    }
+    j -= R;
+    if (j < n_3) {                                               // dCP_A3[h] = sum_d dKR[h,d] (.) A4[d]
+      if (a.g_kr != nullptr) {
+        const int r = static_cast<int>(j % R), h = static_cast<int>(j / R);
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc = fmaf(a.g_kr[static_cast<long>(h * D + d) * a.ld_kr + r], a.A4[d * R + r], acc);
+        a.dA3[j] = acc;
+      }
+      continue;
+    }
+    j -= n_3;
+    if (j < n_4) {                                               // dCP_A4[d] = sum_h dKR[h,d] (.) A3[h]
+      if (a.g_kr != nullptr) {
+        const int r = static_cast<int>(j % R), d = static_cast<int>(j / R);
+        float acc = 0.f;
+        for (int h = 0; h < H; ++h) acc = fmaf(a.g_kr[static_cast<long>(h * D + d) * a.ld_kr + r], a.A3[h * R + r], acc);
+        a.dA4[j] = acc;
+      }
+      continue;
+    }
+    j -= n_4;
+    if (j < n_p) {                                               // dCP_P1[pi[l]] += s_a dcs_proj[l] (.) R2
+      if (a.g_cs_proj != nullptr) {
+        const int r = static_cast<int>(j % R), l = static_cast<int>(j / R);
+        atomicAdd(a.dP1 + static_cast<long>(a.pi[l]) * R + r, a.s_a[l] * a.g_cs_proj[static_cast<long>(l) * a.ld_cs_proj + r] * a.R2[r]);
+      }
+      continue;
+    }
+    j -= n_p;
+    if (j < n_1) {                                               // dCP_P1[mi[l]+k] += s_m dcs_fc1[l,k] (.) R2
+      if (a.g_cs_fc1 != nullptr) {
+        const int r = static_cast<int>(j % R), k = static_cast<int>((j / R) % 4), l = static_cast<int>(j / (4 * R));
+        atomicAdd(a.dP1 + static_cast<long>(a.mi[l] + k) * R + r,
+                  a.s_m[l] * a.g_cs_fc1[(static_cast<long>(l) * 4 + k) * a.ld_cs_fc1 + r] * a.R2[r]);
+      }
+      continue;
+    }
+    j -= n_1;
+    if (j < n_1) {                                               // dCP_P1[mi[l]+4+k] += sum_b dA_fc2[l,k,b] (.) P2[b]
+      if (a.g_a_fc2 != nullptr) {
+        const int r = static_cast<int>(j % R), k = static_cast<int>((j / R) % 4), l = static_cast<int>(j / (4 * R));
+        const float* g = a.g_a_fc2 + (static_cast<long>(l) * 4 + k) * C * a.ld_a_fc2 + r;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        int bcol = 0;
+        for (; bcol + 3 < C; bcol += 4) {
+          acc0 = fmaf(g[static_cast<long>(bcol) * a.ld_a_fc2], a.P2[static_cast<long>(bcol) * R + r], acc0);
+          acc1 = fmaf(g[static_cast<long>(bcol + 1) * a.ld_a_fc2], a.P2[static_cast<long>(bcol + 1) * R + r], acc1);
+          acc2 = fmaf(g[static_cast<long>(bcol + 2) * a.ld_a_fc2], a.P2[static_cast<long>(bcol + 2) * R + r], acc2);
+          acc3 = fmaf(g[static_cast<long>(bcol + 3) * a.ld_a_fc2], a.P2[static_cast<long>(bcol + 3) * R + r], acc3);
+        }
+        for (; bcol < C; ++bcol) acc0 = fmaf(g[static_cast<long>(bcol) * a.ld_a_fc2], a.P2[static_cast<long>(bcol) * R + r], acc0);
+        atomicAdd(a.dP1 + static_cast<long>(a.mi[l] + 4 + k) * R + r, (acc0 + acc1) + (acc2 + acc3));
+      }
+      continue;
+    }
+    j -= n_1;
+    if (j < n_2) {                                               // dCP_P2[b] (a_fc2 share) = sum_{l,k} dA_fc2[l,k,b] (.) P1[mi[l]+4+k]
+      if (a.g_a_fc2 != nullptr) {
+        const int r = static_cast<int>(j % R), bcol = static_cast<int>(j / R);
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l)
+          for (int k = 0; k < 4; ++k)
+            acc = fmaf(a.g_a_fc2[((static_cast<long>(l) * 4 + k) * C + bcol) * a.ld_a_fc2 + r],
+                       a.P1[static_cast<long>(a.mi[l] + 4 + k) * R + r], acc);
+        a.dP2[j] = acc;
+      }
+      continue;
+    }
+    j -= n_2;
+    if (j < R) {                                                 // dCP_R2
+      const int r = static_cast<int>(j);
+      float acc = 0.f;
+      for (int l = 0; l < L; ++l) {
+        if (a.g_cs_proj != nullptr)
+          acc = fmaf(a.s_a[l] * a.g_cs_proj[static_cast<long>(l) * a.ld_cs_proj + r], a.P1[static_cast<long>(a.pi[l]) * R + r], acc);
+        if (a.g_cs_fc1 != nullptr)
+          for (int k = 0; k < 4; ++k)
+            acc = fmaf(a.s_m[l] * a.g_cs_fc1[(static_cast<long>(l) * 4 + k) * a.ld_cs_fc1 + r],
+                       a.P1[static_cast<long>(a.mi[l] + k) * R + r], acc);
+        if (a.g_cs_fc2 != nullptr) acc = fmaf(a.s_m[l], a.g_cs_fc2[static_cast<long>(l) * a.ld_cs_fc2 + r], acc);
+      }
+      a.dR2[r] = acc;
+      continue;
+    }
+    j -= R;
+    {                                                            // dCP_bias1 [C], dCP_bias2 [4C], dCP_bias3 [C]
+      const float* g; const float* sc; float* out; int width; long col;
+      if (j < C) { g = a.g_b_proj; sc = a.s_a; out = a.dbias1; width = C; col = j; }
+      else if (j < 5L * C) { g = a.g_b_fc1; sc = a.s_m; out = a.dbias2; width = 4 * C; col = j - C; }
+      else { g = a.g_b_fc2; sc = a.s_m; out = a.dbias3; width = C; col = j - 5L * C; }
+      if (g != nullptr) {
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l) acc = fmaf(sc[l], g[static_cast<long>(l) * width + col], acc);
+        out[col] = acc;
+      }
+    }
+  }
+}
+
+int stage_launch(const StageArgs& a, int backward, cudaStream_t st) {
+  if (a.R <= 0 || a.Rp < a.R || a.C <= 0 || a.D <= 0 || a.C % a.D != 0 || a.L <= 0) return -71;
+  long total;
+  if (!backward) total = static_cast<long>(a.C) * a.R * (1 + 4L * a.L) + static_cast<long>(a.L) * (9L * a.R + 6L * a.C);
+  else total = static_cast<long>(a.L) * 12 * a.R + 2L * a.R + static_cast<long>(a.C / a.D + a.D + a.C) * a.R + 6L * a.C;
+  long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (backward) stage_bwd_kernel<<<static_cast<int>(grid), 256, 0, st>>>(a);
+  else stage_fwd_kernel<<<static_cast<int>(grid), 256, 0, st>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -72;
+}
+
 // ---------------------------------------------------------------- eval-mode merge
 // Weff[n, k] = W[n, k] + sum_r (Bf[n mod w, r] * cs[n / w, r]) * A[k, r]      W fp32 -> Weff bf16
 template <int R>

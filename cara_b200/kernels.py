@@ -175,6 +175,23 @@ def factor_operands(F, Rp):
     return ext, t2
 
 
+def stage_terms(desc_fill, backward, anchor):
+    """One launch of the CP-factor staging (backward = 0) or of its chain rule (1); ``desc_fill`` maps field names of
+    ``cara_stage_desc`` to ints / tensors (None = NULL).  ``anchor`` is any CUDA tensor of the call (device, stream)."""
+    st = _prep(anchor)
+    d = L.StageDesc()
+    for k, v in desc_fill.items():
+        if v is None:
+            continue
+        if isinstance(v, torch.Tensor):
+            if not v.is_cuda:
+                raise L.CaraLibraryError("cara_stage_terms needs CUDA tensors (no CPU fallback)")
+            setattr(d, k, v.data_ptr())
+        else:
+            setattr(d, k, int(v))
+    L.check(L.lib().cara_stage_terms(C.byref(d), int(backward), st), "cara_stage_terms")
+
+
 def adapter_rows_fwd(x, a_t2, scales):
     """x bf16 [M,K]; a_t2 bf16 [2Rp,K]; scales fp32 [S,Rp] -> (T fp32 [M,Rp], Uhat bf16 [M,S*3Rp])."""
     st = _prep(x)

@@ -1,8 +1,9 @@
 """Per-step staging of the CP factors into the per-projection terms the kernels consume.
 
 SURVEY Appendix A.1 table: every adapted projection is  Y = X W^T + b + s ((X A (.) c) B^T + beta).  Here the
-twelve ``CP_*`` parameters of the root model (cara.py:112-125) are turned -- with differentiable fp32 torch
-ops over tensors of a few thousand elements, batched over all layers -- into, per layer and projection,
+twelve ``CP_*`` parameters of the root model (cara.py:112-125) are turned -- by ONE differentiable launch
+(``StageFunction`` -> ``cara_stage_terms``; its backward is one more launch), batched over all layers -- into, per layer
+and projection,
 ``A`` [K,R], ``cs = s*c`` [slices,R], ``B`` [N/slices,R] and ``bias = b + s*beta``; autograd carries the
 kernels' gradients w.r.t. these terms back to the ``CP_*`` parameters (SURVEY A.2 chain rule).  The row maps
 follow the reference's own indices: ``CP_A1[attn_idx : attn_idx+3]`` (cara.py:26), ``CP_P1[idx]`` (:51),
@@ -33,6 +34,77 @@ class Terms:
         if self.sink is not None:
             return self.stacked + (self.sink,)
         return self.A, self.cs, self.B, self.bias, None
+
+
+_STAGED = ("kr", "cs_qkv", "cs_proj", "cs_fc1", "a_fc2", "cs_fc2", "b_proj", "b_fc1", "b_fc2")
+_PARAMS = ("A1", "A3", "A4", "P1", "P2", "R1", "R2", "bias1", "bias2", "bias3")
+
+
+def _rows_with_pitch(g):
+    """An R-wide gradient as (tensor, row pitch): dense tensors have pitch R; the ``[..., :R]`` views into the Rp-wide
+    gradient sink (ops.GradSink.release) are passed as they are with pitch Rp; anything else is made dense."""
+    if g.stride(-1) != 1:
+        g = g.contiguous()
+    if g.is_contiguous():
+        return g, g.shape[-1]
+    pitch = expect = g.stride(-2)
+    for i in range(g.dim() - 2, -1, -1):
+        if g.stride(i) != expect:
+            return g.contiguous(), g.shape[-1]
+        expect *= g.shape[i]
+    return g, pitch
+
+
+class StageFunction(torch.autograd.Function):
+    """CP_* parameters -> the nine staged tensors (one ``cara_stage_terms`` launch) and, in backward, the chain rule
+    of SURVEY A.2 back to the parameters (one more launch) -- instead of ~30 + ~60 tiny torch kernels per step.
+    ``const`` = dict(ai, pi, mi int32 [L]; s_a, s_m fp32 [L]; fb_proj [L,C], fb_fc1 [L,4C], fb_fc2 [L,C]; D; Rp; pads =
+    the four zero-padded [.., Rp] outputs to fill)."""
+
+    @staticmethod
+    def forward(ctx, A1, A3, A4, P1, P2, R1, R2, bias1, bias2, bias3, const):
+        ps = [t.detach().float().contiguous() for t in (A1, A3, A4, P1, P2, R1, R2, bias1, bias2, bias3)]
+        R, C, L_ = ps[0].shape[1], ps[4].shape[0], const["ai"].shape[0]
+        dev = ps[0].device
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=F32)                 # noqa: E731
+        out = {"kr": new(C, R), "cs_qkv": new(L_, 3, R), "cs_proj": new(L_, 1, R), "cs_fc1": new(L_, 4, R),
+               "a_fc2": new(L_, 4 * C, R), "cs_fc2": new(L_, 1, R), "b_proj": new(L_, C), "b_fc1": new(L_, 4 * C),
+               "b_fc2": new(L_, C)}
+        fill = {"R": R, "Rp": const["Rp"], "C": C, "D": const["D"], "L": L_}
+        fill.update(dict(zip(_PARAMS, ps)))
+        fill.update({k: const[k] for k in ("ai", "pi", "mi", "s_a", "s_m", "fb_proj", "fb_fc1", "fb_fc2")})
+        fill.update(out)
+        fill.update({k + "_pad": v for k, v in const["pads"].items()})
+        K.stage_terms(fill, 0, ps[0])
+        ctx.const, ctx.dims = const, (R, C, L_)
+        ctx.save_for_backward(*ps)
+        res = tuple(out[k] for k in _STAGED)
+        return res
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ps = ctx.saved_tensors
+        const = ctx.const
+        R, C, L_ = ctx.dims
+        dev = ps[0].device
+        sizes = [ps[0].numel(), ps[1].numel(), ps[2].numel(), ps[3].numel(), ps[4].numel(), R, R, C, 4 * C, C]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=F32)            # one zero fill for all ten outputs
+        outs = [v.view(p.shape) for v, p in zip(torch.split(flat, sizes), ps)]
+        fill = {"R": R, "Rp": const["Rp"], "C": C, "D": const["D"], "L": L_}
+        fill.update(dict(zip(_PARAMS, ps)))
+        fill.update({k: const[k] for k in ("ai", "pi", "mi", "s_a", "s_m")})
+        for name, g in zip(_STAGED, grads):
+            if g is None:
+                continue
+            g = g if g.dtype == F32 else g.float()
+            if name.startswith("b_"):
+                g = g.contiguous()
+            else:
+                g, fill["ld_" + name] = _rows_with_pitch(g)
+            fill["g_" + name] = g
+        fill.update(dict(zip(("dA1", "dA3", "dA4", "dP1", "dP2", "dR1", "dR2", "dbias1", "dbias2", "dbias3"), outs)))
+        K.stage_terms(fill, 1, ps[0])
+        return tuple(outs) + (None,)
 
 
 def _modules(model):
@@ -71,32 +143,33 @@ def staged(model):
     icache = model.__dict__.get("_cara_stage_idx")
     if icache is None or icache[0] != ikey:
         icache = (ikey,
-                  torch.tensor([int(m.attn_idx) for m in attn], device=dev),
-                  torch.tensor([int(m.idx) for m in attn], device=dev),
-                  torch.tensor([int(m.idx) for m in mlp], device=dev),
-                  torch.tensor([float(m.s) for m in attn], device=dev, dtype=F32).view(La, 1, 1),
-                  torch.tensor([float(m.s) for m in mlp], device=dev, dtype=F32).view(Lm, 1, 1),
-                  torch.arange(3, device=dev), torch.arange(4, device=dev))
+                  torch.tensor([int(m.attn_idx) for m in attn], device=dev, dtype=torch.int32),
+                  torch.tensor([int(m.idx) for m in attn], device=dev, dtype=torch.int32),
+                  torch.tensor([int(m.idx) for m in mlp], device=dev, dtype=torch.int32),
+                  torch.tensor([float(m.s) for m in attn], device=dev, dtype=F32),
+                  torch.tensor([float(m.s) for m in mlp], device=dev, dtype=F32))
         model.__dict__["_cara_stage_idx"] = icache
-    _, ai, pi, mi, s_a, s_m, r3, r4 = icache
+    _, ai, pi, mi, s_a, s_m = icache
 
-    kr_attn = (f["CP_A3"][:, None, :] * f["CP_A4"][None, :, :]).reshape(C, R)            # B of qkv
-    cs_qkv = s_a * (f["CP_R1"] * f["CP_A1"][ai[:, None] + r3])                            # [La,3,R]
-    cs_proj = s_a * (f["CP_R2"] * f["CP_P1"][pi][:, None, :])                             # [La,1,R]
-    cs_fc1 = s_m * (f["CP_R2"] * f["CP_P1"][mi[:, None] + r4])                            # [Lm,4,R]
-    a_fc2 = (f["CP_P1"][mi[:, None] + 4 + r4][:, :, None, :] * f["CP_P2"][None, None]).reshape(Lm, 4 * C, R)
-    cs_fc2 = s_m * f["CP_R2"].view(1, 1, R).expand(Lm, 1, R)
+    if La != Lm:
+        raise NotImplementedError("CaRA staging expects one Attention and one Mlp per block")
     # the frozen biases never change during fine-tuning: stack them once per (pointer, version) set
     bkey = key[4]
     bcache = model.__dict__.get("_cara_stage_bias")
     if bcache is None or bcache[0] != bkey:
-        bcache = (bkey, torch.stack([m.proj.bias.detach().float() for m in attn]),
-                  torch.stack([m.fc1.bias.detach().float() for m in mlp]),
-                  torch.stack([m.fc2.bias.detach().float() for m in mlp]))
+        bcache = (bkey, torch.stack([m.proj.bias.detach().float() for m in attn]).contiguous(),
+                  torch.stack([m.fc1.bias.detach().float() for m in mlp]).contiguous(),
+                  torch.stack([m.fc2.bias.detach().float() for m in mlp]).contiguous())
         model.__dict__["_cara_stage_bias"] = bcache
-    b_proj = bcache[1] + s_a.view(La, 1) * f["CP_bias1"]
-    b_fc1 = bcache[2] + s_m.view(Lm, 1) * f["CP_bias2"]
-    b_fc2 = bcache[3] + s_m.view(Lm, 1) * f["CP_bias3"]
+    # one launch: the nine staged tensors + the Rp-padded copies of the cs terms the kernels read
+    zp = lambda *shape: torch.zeros(shape, device=dev, dtype=F32)                      # noqa: E731
+    csq, csp, cs1, cs2 = zp(La, 3, Rp), zp(La, 1, Rp), zp(Lm, 4, Rp), zp(Lm, 1, Rp)
+    const = {"ai": ai, "pi": pi, "mi": mi, "s_a": s_a, "s_m": s_m, "fb_proj": bcache[1], "fb_fc1": bcache[2],
+             "fb_fc2": bcache[3], "D": C // P["CP_A3"].shape[0], "Rp": Rp,
+             "pads": {"cs_qkv": csq, "cs_proj": csp, "cs_fc1": cs1, "cs_fc2": cs2}}
+    kr_attn, cs_qkv, cs_proj, cs_fc1, a_fc2, cs_fc2, b_proj, b_fc1, b_fc2 = StageFunction.apply(
+        f["CP_A1"], f["CP_A3"], f["CP_A4"], f["CP_P1"], f["CP_P2"], f["CP_R1"], f["CP_R2"], f["CP_bias1"], f["CP_bias2"],
+        f["CP_bias3"], const)
 
     with torch.no_grad():
         a2_pad, a2_t = K.factor_operands(f["CP_A2"], Rp)
@@ -104,8 +177,6 @@ def staged(model):
         p2_pad, p2_t = K.factor_operands(f["CP_P2"], Rp)
         p3_pad, p3_t = K.factor_operands(f["CP_P3"], Rp)
         afc2_pad, afc2_t = K.factor_operands(a_fc2, Rp)
-        pad = lambda t: torch.nn.functional.pad(t.detach(), (0, Rp - R)).contiguous()  # noqa: E731
-        csq, csp, cs1, cs2 = pad(cs_qkv), pad(cs_proj), pad(cs_fc1), pad(cs_fc2)
 
     # gradients on: every projection's backward accumulates into one zero-filled sink (ops.GradSink)
     sink = GradSink(max(La, Lm), C, Rp, dev) if (grad_on and La == Lm) else None

@@ -164,6 +164,30 @@ CARA_API int cara_assemble_tokens(const void* pe, const float* cls, const float*
 CARA_API int cara_factor_operands(const float* F, void* ext, void* t2, long batch, int rows, int R, int Rp,
                                   void* stream);
 
+/* Per-step staging of the twelve CP_* parameters (cara.py:112-125) into the per-layer, per-projection terms of
+ * SURVEY A.1 -- what the reference does implicitly when it slices CP_A1 / CP_P1 rows and calls tl.cp_to_tensor
+ * (cara.py:26-34, 51-56, 72-80, 88-91) -- and (backward = 1) the chain rule of SURVEY A.2 back to the parameters.
+ * One launch each way.  All fp32, contiguous unless a pitch is given; L layers, C = H * D, rank R (Rp = padded).
+ *   forward :  kr [C,R] = KR(A3, A4);  cs_qkv [L,3,R] = s_a R1 A1[ai+k];  cs_proj [L,R] = s_a R2 P1[pi];
+ *              cs_fc1 [L,4,R] = s_m R2 P1[mi+k];  a_fc2 [L,4C,R] = P1[mi+4+k] (x) P2;  cs_fc2 [L,R] = s_m R2;
+ *              b_proj / b_fc1 / b_fc2 = frozen bias + s * CP_bias1/2/3;  *_pad = the cs terms in [.., Rp] rows
+ *              (caller zero-fills the padding once).
+ *   backward:  g_* (NULL = no gradient; ld_* = row pitch of the R-wide ones) -> dA1, dA3, dA4, dP1, dP2 (the a_fc2
+ *              share only), dR1, dR2, dbias1..3, all zero-filled by the caller (indexed rows are added atomically). */
+typedef struct cara_stage_desc {
+  int R, Rp, C, D, L;
+  const float *A1, *A3, *A4, *P1, *P2, *R1, *R2, *bias1, *bias2, *bias3;
+  const int *ai, *pi, *mi;
+  const float *s_a, *s_m;
+  const float *fb_proj, *fb_fc1, *fb_fc2;
+  float *kr, *cs_qkv, *cs_proj, *cs_fc1, *a_fc2, *cs_fc2, *b_proj, *b_fc1, *b_fc2;
+  float *cs_qkv_pad, *cs_proj_pad, *cs_fc1_pad, *cs_fc2_pad;
+  const float *g_kr, *g_cs_qkv, *g_cs_proj, *g_cs_fc1, *g_a_fc2, *g_cs_fc2, *g_b_proj, *g_b_fc1, *g_b_fc2;
+  long ld_kr, ld_cs_qkv, ld_cs_proj, ld_cs_fc1, ld_a_fc2, ld_cs_fc2;
+  float *dA1, *dA3, *dA4, *dP1, *dP2, *dR1, *dR2, *dbias1, *dbias2, *dbias3;
+} cara_stage_desc;
+CARA_API int cara_stage_terms(const cara_stage_desc* d, int backward, void* stream);
+
 /* Eval-mode merge (the reference re-materialises the delta every forward, cara.py:27,52,76,88):
  *   Weff[n,k] = W[n,k] + sum_r Bf[n mod w, r] cs[n / w, r] A[k, r],  W fp32 [N,K] -> Weff bf16 [N,K]. */
 CARA_API int cara_merge_weights(const float* W, const float* A, const float* Bf, const float* cs, void* Weff, int N,

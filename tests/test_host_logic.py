@@ -36,16 +36,38 @@ def _small():
     return vit, st, g
 
 
-def test_staging_matches_oracle_factoring_and_grad_chain(monkeypatch):
-    """staged (A, cs, B, bias) == oracle.adapter_terms (A.1) and autograd through the staging reproduces the
-    oracle's chain rule to the CP parameters (A.2).  The product's ``factor_operands`` is a CUDA kernel with no CPU
-    path; on this CPU-only run the test substitutes the torch formulation (tests/_torch_ref.py), which
-    test_factor_operands_kernel_matches_torch_formulation (-m gpu) holds bit-identical to the kernel."""
-    from cara_b200 import kernels as K
-    from cara_b200 import staging
+def test_torch_staging_reference_matches_oracle_factoring():
+    """tests/_torch_ref.stage_terms -- the torch formulation the GPU test checks ``cara_stage_terms`` (and its backward)
+    against -- reproduces the oracle's factoring of every projection on the CPU."""
     from tests import _torch_ref
-    monkeypatch.setattr(K, "factor_operands", _torch_ref.factor_operands)
+    g = O.Geometry(embed_dim=256, depth=2, num_heads=4, rank=8, num_classes=7)
+    st = O.synthetic_state(g, dtype=torch.float32)
+    L_, C = g.depth, g.embed_dim
+    s = 2.5
+    P = {k: st[k] for k in st if k.startswith("CP_")}
+    ai, pi, mi = torch.arange(L_) * 3, torch.arange(L_) * 9, torch.arange(L_) * 9 + 1      # cara.py:150-162 row maps
+    sc = torch.full((L_,), s)
+    fb = [torch.stack([st["blocks.%d.%s.bias" % (l, n)] for l in range(L_)]) for n in ("attn.proj", "mlp.fc1", "mlp.fc2")]
+    kr, cs_qkv, cs_proj, cs_fc1, a_fc2, cs_fc2, b_proj, b_fc1, b_fc2 = _torch_ref.stage_terms(P, ai, pi, mi, sc, sc, *fb)
+    for l in range(L_):
+        for which, A_, cs_, B_, bias_ in (("qkv", st["CP_A2"], cs_qkv[l], kr, None), ("proj", st["CP_P3"], cs_proj[l], st["CP_P2"], b_proj[l]),
+                                          ("fc1", st["CP_P3"], cs_fc1[l], st["CP_P2"], b_fc1[l]),
+                                          ("fc2", a_fc2[l], cs_fc2[l], st["CP_P3"], b_fc2[l])):
+            A, c, B, beta = O.adapter_terms(st, g, l, which)
+            assert torch.allclose(A_, A, atol=1e-6) and torch.allclose(B_, B, atol=1e-6) and torch.allclose(cs_, s * c, atol=1e-6), which
+            if beta is not None:
+                key = {"proj": "attn.proj", "fc1": "mlp.fc1", "fc2": "mlp.fc2"}[which]
+                assert torch.allclose(bias_, st["blocks.%d.%s.bias" % (l, key)] + s * beta, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_staging_matches_oracle_factoring_and_grad_chain():
+    """staged (A, cs, B, bias) == oracle.adapter_terms (A.1) and autograd through the staging (one ``cara_stage_terms``
+    launch each way) reproduces the oracle's chain rule to the CP parameters (A.2); operand layouts; cache behaviour."""
+    from cara_b200 import staging
     vit, st, g = _small()
+    vit = vit.cuda()
+    st = {k: v.cuda() for k, v in st.items()}
     amap, mmap = staging.staged(vit)
     s = 2.5
     torch.manual_seed(0)
@@ -60,6 +82,7 @@ def test_staging_matches_oracle_factoring_and_grad_chain(monkeypatch):
             assert torch.allclose(t.A, A.detach(), atol=1e-6) and torch.allclose(t.B, B.detach(), atol=1e-6)
             assert torch.allclose(t.cs, (s * c).detach(), atol=1e-6), which
             assert t.ops.cs_pad.shape == (c.shape[0], 16) and t.ops.a_t2.shape == (32, A.shape[0])
+            assert torch.allclose(t.ops.cs_pad[:, :8], (s * c).detach(), atol=1e-6) and float(t.ops.cs_pad[:, 8:].abs().max()) == 0
             hi = A.detach().bfloat16()
             assert torch.equal(t.ops.a_ext[:, :8], hi) and torch.equal(t.ops.a_ext[:, 16:24], hi)
             assert torch.equal(t.ops.a_ext[:, 32:40], (A.detach() - hi.float()).bfloat16())
@@ -89,6 +112,53 @@ def test_staging_matches_oracle_factoring_and_grad_chain(monkeypatch):
         assert staging.staged(vit)[0] is frozen
         vit.CP_R1.add_(1.0)
         assert staging.staged(vit)[0] is not frozen
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L_,C,H,R,sink", [(2, 256, 4, 8, False), (12, 768, 12, 16, True), (3, 1024, 16, 32, True), (2, 1280, 16, 20, False)])
+def test_stage_terms_kernel_forward_and_backward_vs_torch(L_, C, H, R, sink):
+    """``cara_stage_terms`` (forward and chain rule) against the torch formulation and its autograd, with dense
+    gradients and with gradients that are [..., :R] views into Rp-wide buffers (what ops.GradSink hands back)."""
+    from cara_b200 import kernels as K
+    from cara_b200 import staging
+    from tests import _torch_ref
+    gen = torch.Generator().manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, generator=gen).cuda()                              # noqa: E731
+    D, Rp = C // H, K.round_rank(R)
+    P = {"CP_A1": rnd(3 * L_, R), "CP_A2": rnd(C, R), "CP_A3": rnd(H, R), "CP_A4": rnd(D, R), "CP_P1": rnd(9 * L_, R),
+         "CP_P2": rnd(C, R), "CP_P3": rnd(C, R), "CP_R1": rnd(R), "CP_R2": rnd(R), "CP_bias1": rnd(C), "CP_bias2": rnd(4 * C),
+         "CP_bias3": rnd(C)}
+    ai, pi, mi = torch.arange(L_).cuda() * 3, torch.arange(L_).cuda() * 9, torch.arange(L_).cuda() * 9 + 1
+    s_a, s_m = rnd(L_).abs() + 0.5, rnd(L_).abs() + 0.5
+    fb = [rnd(L_, C), rnd(L_, 4 * C), rnd(L_, C)]
+    names = ("CP_A1", "CP_A3", "CP_A4", "CP_P1", "CP_P2", "CP_R1", "CP_R2", "CP_bias1", "CP_bias2", "CP_bias3")
+    leaf_k = {n: P[n].clone().requires_grad_(True) for n in names}
+    leaf_t = {n: P[n].clone().requires_grad_(True) for n in names}
+    pads = {"cs_qkv": torch.zeros(L_, 3, Rp).cuda(), "cs_proj": torch.zeros(L_, 1, Rp).cuda(), "cs_fc1": torch.zeros(L_, 4, Rp).cuda(),
+            "cs_fc2": torch.zeros(L_, 1, Rp).cuda()}
+    const = {"ai": ai.int(), "pi": pi.int(), "mi": mi.int(), "s_a": s_a, "s_m": s_m, "fb_proj": fb[0], "fb_fc1": fb[1],
+             "fb_fc2": fb[2], "D": D, "Rp": Rp, "pads": pads}
+    got = staging.StageFunction.apply(*[leaf_k[n] for n in names], const)
+    Pt = dict(P); Pt.update(leaf_t)
+    want = _torch_ref.stage_terms(Pt, ai, pi, mi, s_a, s_m, *fb)
+    for name, a, b in zip(staging._STAGED, got, want):
+        assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-6, atol=1e-7), name
+    for k in pads:
+        w = dict(zip(staging._STAGED, want))[k]
+        assert torch.allclose(pads[k][..., :R], w, rtol=1e-6, atol=1e-7) and float(pads[k][..., R:].abs().max() if Rp > R else 0.0) == 0.0
+    grads = []
+    for a in want:
+        g = rnd(*a.shape)
+        if sink and a.shape[-1] == R and a.dim() >= 2 and not (a.dim() == 2 and a.shape[0] == L_ and a.shape[1] in (C, 4 * C)):
+            buf = torch.zeros(*a.shape[:-1], Rp).cuda()
+            buf[..., :R] = g
+            grads.append((buf[..., :R], g))
+        else:
+            grads.append((g, g))
+    torch.autograd.backward(list(got), [g[0] for g in grads])
+    torch.autograd.backward(list(want), [g[1] for g in grads])
+    for n in names:
+        assert torch.allclose(leaf_k[n].grad, leaf_t[n].grad, rtol=2e-4, atol=1e-5), (n, float((leaf_k[n].grad - leaf_t[n].grad).abs().max()))
 
 
 def test_state_dict_schema_roundtrip():
