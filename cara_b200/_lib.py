@@ -9,10 +9,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcara_b200.so")
 
-EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_DGELU, EPI_DELTA = 0, 1, 2, 3
 SIDE_NONE, SIDE_FWD, SIDE_BWD = 0, 1, 2
 SYNC_WORDS = 16386
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class GemmDesc(C.Structure):
@@ -33,6 +33,8 @@ class GemmDesc(C.Structure):
         ("side_scales", C.c_void_p), ("side_T", C.c_void_p),
         ("side_U", C.c_void_p), ("side_ldu", C.c_long),
         ("side_dc", C.c_void_p), ("sync_ws", C.c_void_p),
+        ("aux2", C.c_void_p), ("ldaux2", C.c_int),
+        ("delta", C.c_void_p), ("seq_n", C.c_int),
     ]
 
 

@@ -49,6 +49,8 @@ int cara_gemm_cp(const cara_gemm_desc* d, void* stream) {
   g.side_scales = d->side_scales; g.side_T = d->side_T;
   g.side_U = static_cast<__nv_bfloat16*>(d->side_U); g.side_ldu = d->side_ldu;
   g.side_dc = d->side_dc; g.sync = static_cast<unsigned*>(d->sync_ws);
+  g.aux2 = static_cast<const __nv_bfloat16*>(d->aux2); g.ldaux2 = d->ldaux2;
+  g.delta = d->delta; g.seq_n = d->seq_n;
   int rc = cara::gemm_cp_launch(g, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(rc, "cara_gemm_cp: launch failed / bad arguments");
   return 0;
@@ -108,6 +110,8 @@ int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float*
   cara::AttnArgs a{static_cast<const bf16*>(qkv), static_cast<bf16*>(const_cast<void*>(o)),
                    static_cast<bf16*>(const_cast<void*>(o_lo)), const_cast<float*>(lse),
                    static_cast<const bf16*>(d_o), static_cast<bf16*>(dqkv), delta_ws, B, N, H, D, scale};
+  if (o == nullptr && (D != 64 || N > 256 || delta_ws == nullptr))
+    return fail(-50, "cara_attn_bwd: a precomputed delta (o == NULL) needs D = 64, N <= 256");
   CARA_RET(cara::attn_bwd_launch(a, CARA_STREAM(stream)), "cara_attn_bwd");
 }
 int cara_gelu_f32(const float* dy, const float* x, float* out, long n, void* stream) {

@@ -475,7 +475,12 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t st) {
   return -50;
 }
 int attn_bwd_launch(const AttnArgs& a, cudaStream_t st) {
-  if (a.B <= 0 || a.N <= 0 || a.H <= 0 || a.o_lo == nullptr) return -50;
+  if (a.B <= 0 || a.N <= 0 || a.H <= 0) return -50;
+  if (a.o == nullptr) {                                         // delta already in a.delta (EPI_DELTA of the proj dX GEMM)
+    const int rc = (attn_tc_mask() & 2) ? attn_bwd_tc_launch(a, st) : 1;
+    return rc == 1 ? -50 : rc;
+  }
+  if (a.o_lo == nullptr) return -50;
   if (attn_tc_mask() & 2) {
     const int rc = attn_bwd_tc_launch(a, st);
     if (rc <= 0) return rc;

@@ -637,7 +637,9 @@ int attn_bwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
   }
   int grid = a.B * a.H;
   if (grid > 148) grid = 148;
-  if (launch_pdl_f<2>(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, a.d_o, a.o, a.o_lo, a.delta,
+  // a.o == nullptr: delta was written by the output projection's dX GEMM (EPI_DELTA), no pre-pass
+  if (a.o != nullptr &&
+      launch_pdl_f<2>(attn_delta_kernel, dim3(static_cast<int>((rows + 7) / 8)), dim3(256), 0, st, a.d_o, a.o, a.o_lo, a.delta,
                  static_cast<int>(rows), a.N, a.H) != cudaSuccess)
     return -53;
   return launch_pdl_f<2>(attn_bwd_tc_kernel, dim3(grid), dim3(TCB_THREADS), smem, st, map_qkv, map_do, a, npad, qk_pairs) ==

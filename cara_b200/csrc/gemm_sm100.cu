@@ -56,8 +56,9 @@ constexpr int TMEM_COLS = 512;                  // 2 accumulators x 256 fp32 col
 constexpr int EC = 64;                          // epilogue step: 64 output columns = one 128-B swizzle row
 constexpr int EBUF = 32 * EC * 2;               // 4 KB staging buffer: 32 rows x 128 B; two per epilogue warp
 constexpr int SIDE_RED = 4 * 32;                // dcs partial sums of this CTA (slices x rank)
-__host__ __device__ constexpr int num_epi_warps(int epi) { return epi == EPI_NONE ? 4 : 8; }
-__host__ __device__ constexpr int epi_bufs(int epi) { return epi == EPI_NONE ? 2 : 1; }   // staging buffers per warp
+__host__ __device__ constexpr bool light_epi(int epi) { return epi == EPI_NONE || epi == EPI_DELTA; }
+__host__ __device__ constexpr int num_epi_warps(int epi) { return light_epi(epi) ? 4 : 8; }
+__host__ __device__ constexpr int epi_bufs(int epi) { return light_epi(epi) ? 2 : 1; }   // staging buffers per warp
 // SW: four extra warps that drain the side tiles (plain epilogue kind only: the 8-warp GELU kinds are at the register
 // ceiling of 384 threads and keep the stand-alone rows pass)
 __host__ __device__ constexpr int num_threads(int epi, bool sw = false) { return 64 + 32 * num_epi_warps(epi) + (sw ? 128 : 0); }
@@ -306,7 +307,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     mbar_init(sfull_bar, 1);
     mbar_init(sempty_bar, 4);                     // one arrive per side-drain warp
     if (p.tiles_n > 0) tma_prefetch_desc(&mapOut);
-    if (EPI != EPI_NONE) tma_prefetch_desc(&mapAux);
+    if (EPI == EPI_GELU || EPI == EPI_DGELU) tma_prefetch_desc(&mapAux);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -503,6 +504,21 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 4; ++j) ld_global_nc_v8(src + 2 * j, ux[2 * j], ux[2 * j + 1]);
       }
+      // EPI_DELTA: this row's 64 O values (hi, lo) of the current step, requested one step ahead like ux above
+      uint4 oh[EPI == EPI_DELTA ? 8 : 1], ol[EPI == EPI_DELTA ? 8 : 1];
+      const int drow = grow < p.M ? grow : 0;
+      const int d_b = EPI == EPI_DELTA ? drow / p.seq_n : 0;      // sample / token of this thread's row
+      const int d_n = EPI == EPI_DELTA ? drow - d_b * p.seq_n : 0;
+      auto load_o = [&](int col) {
+        const uint4* sh = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(drow) * p.ldaux + col);
+        const uint4* sl = reinterpret_cast<const uint4*>(p.aux2 + static_cast<size_t>(drow) * p.ldaux2 + col);
+#pragma unroll
+        for (int j = 0; j < (EPI == EPI_DELTA ? 4 : 0); ++j) {
+          ld_global_nc_v8(sh + 2 * j, oh[2 * j], oh[2 * j + 1]);
+          ld_global_nc_v8(sl + 2 * j, ol[2 * j], ol[2 * j + 1]);
+        }
+      };
+      if constexpr (EPI == EPI_DELTA) { if (n0 + c_first * EC < p.N) load_o(n0 + c_first * EC); }
       mbar_wait(tfull_bar(as), acc.parity(as));
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -550,6 +566,21 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) w0[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        }
+        if constexpr (EPI == EPI_DELTA) {
+          // delta of (row, head n / 64) from the bf16-rounded outputs -- what the attention backward will read as dO
+          const uint32_t* hw = reinterpret_cast<const uint32_t*>(oh);
+          const uint32_t* lw = reinterpret_cast<const uint32_t*>(ol);
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 g = unpack_bf16(w0[j]), a = unpack_bf16(hw[j]), b = unpack_bf16(lw[j]);
+            d0 = fmaf(g.x, a.x + b.x, d0);
+            d1 = fmaf(g.y, a.y + b.y, d1);
+          }
+          if (grow < p.M && n < p.N)
+            p.delta[(static_cast<size_t>(d_b) * (p.N / EC) + static_cast<size_t>(n / EC)) * p.seq_n + d_n] = d0 + d1;
+          if (ci + 1 < NCH && n + EC < p.N) load_o(n + EC);      // in flight during the staging below
         }
         // earlier TMA stores must have finished READING the buffer this step writes
         if (lane == 0) {
@@ -723,6 +754,8 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
   args.out = d.out; args.ldo = d.ldo;
   args.out2 = d.out2; args.ldo2 = d.ldo2;
   args.aux = d.aux; args.ldaux = d.ldaux;
+  args.aux2 = d.aux2; args.ldaux2 = d.ldaux2;
+  args.delta = d.delta; args.seq_n = d.seq_n;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("CARA_GEMM_DEBUG"); dbg = e != nullptr ? atoi(e) : 0; }
@@ -805,6 +838,12 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
         if (d.aux == nullptr) return -14;
         if ((rc = make_map_bf16(&m.aux, d.aux, d.M, d.N, d.ldaux, 32)) != 0) return rc * 10 - 7;
         break;
+      case EPI_DELTA:
+        if (d.aux == nullptr || d.aux2 == nullptr || d.delta == nullptr || d.seq_n <= 0 || d.M % d.seq_n != 0) return -21;
+        if ((reinterpret_cast<uintptr_t>(d.aux) & 31) != 0 || (reinterpret_cast<uintptr_t>(d.aux2) & 31) != 0 ||
+            ((d.ldaux * 2) & 31) != 0 || ((d.ldaux2 * 2) & 31) != 0)
+          return -21;                                              // 256-bit loads of the O rows
+        break;
       default: return -15;
     }
   }
@@ -814,6 +853,7 @@ int gemm_cp_launch(const GemmDesc& d, cudaStream_t st) {
       e = args.side != SIDE_NONE ? launch_epi<EPI_NONE, true>(m, args, grid, st) : launch_epi<EPI_NONE, false>(m, args, grid, st);
       break;
     case EPI_GELU: e = launch_epi<EPI_GELU, false>(m, args, grid, st); break;
+    case EPI_DELTA: e = launch_epi<EPI_DELTA, false>(m, args, grid, st); break;
     default: e = launch_epi<EPI_DGELU, false>(m, args, grid, st); break;
   }
   return e == cudaSuccess ? 0 : -1000 - static_cast<int>(e);

@@ -6,7 +6,7 @@
 
 namespace cara {
 
-enum GemmEpilogue { EPI_NONE = 0, EPI_GELU = 1, EPI_DGELU = 2 };
+enum GemmEpilogue { EPI_NONE = 0, EPI_GELU = 1, EPI_DGELU = 2, EPI_DELTA = 3 };
 enum GemmSide { SIDE_NONE = 0, SIDE_FWD = 1, SIDE_BWD = 2 };
 
 constexpr int kSyncPanels = 4096;                // M <= 524,288 rows
@@ -24,6 +24,10 @@ struct GemmArgs {
   __nv_bfloat16* out; int ldo;
   __nv_bfloat16* out2; int ldo2;
   const __nv_bfloat16* aux; int ldaux;
+  // EPI_DELTA (the dX GEMM of the attention output projection, head dim 64 = one epilogue step): aux / aux2 = the
+  // attention output O as a bf16 (hi, lo) pair, delta[b, h, n] = sum_d out[m, h*64+d] (O_hi + O_lo)[m, h*64+d], m = b*seq_n + n
+  const __nv_bfloat16* aux2; int ldaux2;
+  float* delta; int seq_n;
   int prefetch;       // 1: L2-prefetch the A0 panel of the CTA's next tile (experiment CARA_GEMM_PREFETCH=1, default 0)
   int debug;          // experiments (CARA_GEMM_DEBUG): 1 = epilogue only drains TMEM, 4 = no output staging, 16 = no side-tile flag wait
   // rank-R side tiles (one per 128-row panel, ahead of the panel's output tiles; see gemm_sm100.cu)
@@ -52,6 +56,8 @@ struct GemmDesc {
   __nv_bfloat16* out; int ldo;
   __nv_bfloat16* out2; int ldo2;
   const __nv_bfloat16* aux; int ldaux;
+  const __nv_bfloat16* aux2; int ldaux2;   // EPI_DELTA
+  float* delta; int seq_n;                // EPI_DELTA
   int epi;
   int num_sms;
   // side tiles (optional): P = [2rp, K0 / (SIDE_BWD ? side_slices : 1)] bf16, rows [hi ; lo] of the transposed factor.

@@ -17,6 +17,9 @@ param_generation = 0  # bumped by adamw_step: parameters changed behind autograd
 # launch instead of the stand-alone rows kernel.  Opt-in: correct (tests/test_kernels_gpu.py::test_gemm_side_tiles_*)
 # but measured slower in the step on B200 (profiles/r02_side_tiles.md).
 side_tiles = __import__("os").environ.get("CARA_SIDE_TILES", "0") == "1"
+# the attention backward's rowsum(dO (.) O) out of the output projection's dX GEMM epilogue (CARA_DELTA_IN_GEMM=0: the
+# stand-alone pre-pass inside cara_attn_bwd)
+delta_in_gemm = __import__("os").environ.get("CARA_DELTA_IN_GEMM", "1") == "1"
 gemm_events = None  # bench.py: list of (start event, end event, algorithmic flops) per fused-projection launch
 _dev = [None]
 
@@ -81,9 +84,10 @@ def _fill_side(d, side, M, K0, device):
 
 
 def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, out=None, out2=None, aux=None,
-            want_pre=True, num_sms=0, side=None):
+            want_pre=True, num_sms=0, side=None, delta=None):
     """out[M,N] = a0[M,K0] b0[N,K0]^T + bias (+ adapter segment a1/b1), see cara_gemm_cp.  ``side`` (a ``Side``):
-    the kernel also computes the low-rank operand -- then ``a1`` must be ``side.U``, which it fills before use."""
+    the kernel also computes the low-rank operand -- then ``a1`` must be ``side.U``, which it fills before use.
+    ``delta`` = (o, o_lo, delta_out [B,H,N] fp32, seq_n) with epi = EPI_DELTA: the attention backward's row term."""
     st = _prep(a0)
     M, K0 = a0.shape
     N = b0.shape[0]
@@ -115,6 +119,12 @@ def gemm_cp(a0, b0, bias=None, a1=None, b1=None, ext_slices=1, epi=L.EPI_NONE, o
     if epi == L.EPI_DGELU:
         assert aux is not None and aux.dtype == BF16 and aux.shape == (M, N)
         d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
+    if epi == L.EPI_DELTA:
+        o_hi, o_lo, dl, seq_n = delta
+        assert o_hi.dtype == BF16 and o_lo.dtype == BF16 and o_hi.shape == (M, N) and o_lo.shape == (M, N)
+        assert dl.dtype == F32 and dl.is_contiguous() and dl.numel() == M * (N // 64) and M % seq_n == 0
+        d.aux, d.ldaux, d.aux2, d.ldaux2 = o_hi.data_ptr(), o_hi.stride(0), o_lo.data_ptr(), o_lo.stride(0)
+        d.delta, d.seq_n = dl.data_ptr(), seq_n
     d.epi, d.num_sms = epi, num_sms
     if gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,13 +257,23 @@ def attn_fwd(qkv, B, N, H, D, scale, train=True):
     return o, o_lo, lse
 
 
-def attn_bwd(qkv, o, o_lo, lse, d_o, B, N, H, D, scale):
+def attn_delta_fusable(N, D):
+    """Shapes whose softmax-backward row term the output projection's dX GEMM can emit (EPI_DELTA): the tcgen05
+    attention path, head dim = one 64-column epilogue step."""
+    return delta_in_gemm and D == 64 and N <= 256 and (int(__import__("os").environ.get("CARA_ATTN_TC", "3")) & 2) != 0
+
+
+def attn_bwd(qkv, o, o_lo, lse, d_o, B, N, H, D, scale, delta=None):
+    """``delta`` [B,H,N] fp32: already computed (cara_gemm_cp, EPI_DELTA) -- the pre-pass over dO and O is skipped."""
     st = _prep(qkv)
     assert d_o.is_contiguous() and d_o.dtype == BF16
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty((B, H, N), device=qkv.device, dtype=F32)
-    L.check(L.lib().cara_attn_bwd(qkv.data_ptr(), o.data_ptr(), o_lo.data_ptr(), lse.data_ptr(), d_o.data_ptr(),
-                                  dqkv.data_ptr(), delta.data_ptr(), B, N, H, D, scale, st), "cara_attn_bwd")
+    pre = delta is not None
+    if not pre:
+        delta = torch.empty((B, H, N), device=qkv.device, dtype=F32)
+    L.check(L.lib().cara_attn_bwd(qkv.data_ptr(), None if pre else o.data_ptr(), None if pre else o_lo.data_ptr(),
+                                  lse.data_ptr(), d_o.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), B, N, H, D, scale, st),
+            "cara_attn_bwd")
     return dqkv
 
 

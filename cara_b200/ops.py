@@ -121,12 +121,13 @@ def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True, train=Tr
     return y, T, U
 
 
-def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink=None):
+def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink=None, delta=None):
     """Returns (dx, dA, dcs, dB, dbias).  ``sink`` = (GradSink, kind, layer): accumulate the factor gradients
-    there and hand them to autograd once per projection kind (see GradSink)."""
-    epi = L.EPI_DGELU if dgelu_aux is not None else L.EPI_NONE
+    there and hand them to autograd once per projection kind (see GradSink).  ``delta`` (output projection of the
+    attention branch only) = (o, o_lo, delta_out, seq_n): the dX GEMM's epilogue also emits rowsum(dX (.) O)."""
+    epi = L.EPI_DGELU if dgelu_aux is not None else (L.EPI_DELTA if delta is not None else L.EPI_NONE)
     if ops is None:
-        dx = K.gemm_cp(G, fz.wt, epi=epi, aux=dgelu_aux) if need_dx else None
+        dx = K.gemm_cp(G, fz.wt, epi=epi, aux=dgelu_aux, delta=delta) if need_dx else None
         return dx, None, None, None, None
     R, Rp, S = ops.rank, ops.rp, ops.slices
     Kin, N = x.shape[1], G.shape[1]
@@ -144,7 +145,7 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink
         # the three readers of G run back to back: for the C-wide projections G (77 MB at ViT-B) stays in the 126 MB L2
         dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
         K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
-        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux) if need_dx else None
+        dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux, delta=delta) if need_dx else None
         K.adapter_cols(x, dT, 1, Rp, out=dA)
         if sink is not None:
             return (dx,) + sink[0].release(sink[1], R, need_bias)
@@ -168,15 +169,17 @@ class CPLinearFunction(torch.autograd.Function):
     """One CP-adapted frozen projection (qkv: cara.py:25-42, proj: cara.py:50-58)."""
 
     @staticmethod
-    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops, sink=None):
+    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops, sink=None, link=None):
         """Without ``sink``: A [K,R], cs [S,R], Bf [N/S,R], bias_eff [N] are this layer's terms.  With ``sink`` =
         (GradSink, kind, layer): cs [L,S,R] and bias_eff [L,N] (and A [L,4C,R] for fc2) are the stacked terms of
-        all layers -- autograd sees one gradient per kind instead of one per layer."""
+        all layers -- autograd sees one gradient per kind instead of one per layer.  ``link`` (an ``AttnLink``, output
+        projection only): x is the attention core's output and this backward's dX GEMM also writes the core's
+        softmax-backward row term (EPI_DELTA)."""
         bias = bias_eff if (bias_eff is None or sink is None) else bias_eff[sink[2]]
         y, T, U = _cp_linear_fwd(x, fz, bias if bias is not None else fz.bias, ops, train=any(ctx.needs_input_grad))
         if sink is not None and any(ctx.needs_input_grad):
             sink[0].pending[sink[1]] += 1
-        ctx.fz, ctx.ops, ctx.sink = fz, ops, sink
+        ctx.fz, ctx.ops, ctx.sink, ctx.link = fz, ops, sink, link
         ctx.save_for_backward(x, T, U)
         return y
 
@@ -184,8 +187,13 @@ class CPLinearFunction(torch.autograd.Function):
     def backward(ctx, G):
         x, T, U = ctx.saved_tensors
         ni = ctx.needs_input_grad
-        dx, dA, dcs, dB, dbias = _cp_linear_bwd(G.contiguous(), x, ctx.fz, ctx.ops, T, U, ni[0], ni[4], sink=ctx.sink)
-        return dx, dA, dcs, dB, dbias, None, None, None
+        link, delta = ctx.link, None
+        if link is not None and link.o_lo is not None and ni[0]:
+            link.delta = torch.empty(link.shape, device=G.device, dtype=F32)
+            delta = (x, link.o_lo, link.delta, link.shape[2])
+        dx, dA, dcs, dB, dbias = _cp_linear_bwd(G.contiguous(), x, ctx.fz, ctx.ops, T, U, ni[0], ni[4], sink=ctx.sink,
+                                                delta=delta)
+        return dx, dA, dcs, dB, dbias, None, None, None, None
 
 
 class CPMlpFunction(torch.autograd.Function):
@@ -221,13 +229,28 @@ class CPMlpFunction(torch.autograd.Function):
         return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None, None, None
 
 
+class AttnLink:
+    """Hand-over between the attention core and the output projection that consumes it: the projection's dX GEMM
+    holds every dO tile in registers, so its epilogue (EPI_DELTA) writes rowsum(dO (.) O) for the core's backward and
+    the separate 232 MB pass over dO and O goes away.  Forward: the core deposits o_lo and the [B,H,N] shape;
+    backward: the projection deposits ``delta``, the core takes it."""
+
+    __slots__ = ("o_lo", "shape", "delta")
+
+    def __init__(self):
+        self.o_lo = self.shape = self.delta = None
+
+
 class AttnCoreFunction(torch.autograd.Function):
     """softmax(q k^T D^-1/2) v on the fused projection's [B,N,3,H,D] output (cara.py:44-48)."""
 
     @staticmethod
-    def forward(ctx, qkv, B, N, H, D, scale):
+    def forward(ctx, qkv, B, N, H, D, scale, link=None):
         o, o_lo, lse = K.attn_fwd(qkv, B, N, H, D, scale, train=ctx.needs_input_grad[0])
         ctx.dims = (B, N, H, D, scale)
+        ctx.link = link
+        if link is not None and o_lo is not None:
+            link.o_lo, link.shape = o_lo, (B, H, N)
         ctx.save_for_backward(qkv, o, o_lo, lse)
         return o
 
@@ -235,7 +258,11 @@ class AttnCoreFunction(torch.autograd.Function):
     def backward(ctx, d_o):
         qkv, o, o_lo, lse = ctx.saved_tensors
         B, N, H, D, scale = ctx.dims
-        return K.attn_bwd(qkv, o, o_lo, lse, d_o.contiguous(), B, N, H, D, scale), None, None, None, None, None
+        delta = None
+        if ctx.link is not None:
+            delta, ctx.link.delta = ctx.link.delta, None
+        return (K.attn_bwd(qkv, o, o_lo, lse, d_o.contiguous(), B, N, H, D, scale, delta=delta),
+                None, None, None, None, None, None)
 
 
 class LayerNormFunction(torch.autograd.Function):

@@ -101,12 +101,13 @@ def attn_forward(mod, x, staged):
     else:
         A, cs, Bf, _, sink = staged[0].autograd_args()
         qkv = ops.CPLinearFunction.apply(h, A, cs, Bf, None, fq, staged[0].ops, sink)
-    o = ops.AttnCoreFunction.apply(qkv, B, N, H, C // H, float(mod.scale))
+    link = ops.AttnLink() if K.attn_delta_fusable(N, C // H) else None
+    o = ops.AttnCoreFunction.apply(qkv, B, N, H, C // H, float(mod.scale), link)
     if staged is None:
-        y = ops.CPLinearFunction.apply(o, None, None, None, None, fp, None)
+        y = ops.CPLinearFunction.apply(o, None, None, None, None, fp, None, None, link)
     else:
         A, cs, Bf, bias, sink = staged[1].autograd_args()
-        y = ops.CPLinearFunction.apply(o, A, cs, Bf, bias, fp, staged[1].ops, sink)
+        y = ops.CPLinearFunction.apply(o, A, cs, Bf, bias, fp, staged[1].ops, sink, link)
     y = y.view(B, N, C)
     return y if x.dtype == BF16 else y.to(x.dtype)
 

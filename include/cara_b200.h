@@ -16,14 +16,14 @@
 extern "C" {
 #endif
 
-#define CARA_B200_ABI_VERSION 2
+#define CARA_B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define CARA_API __attribute__((visibility("default")))
 #else
 #define CARA_API
 #endif
 
-enum cara_epilogue { CARA_EPI_NONE = 0, CARA_EPI_GELU = 1, CARA_EPI_DGELU = 2 };
+enum cara_epilogue { CARA_EPI_NONE = 0, CARA_EPI_GELU = 1, CARA_EPI_DGELU = 2, CARA_EPI_DELTA = 3 };
 
 CARA_API int cara_abi_version(void);
 CARA_API const char* cara_last_error(void);
@@ -38,6 +38,12 @@ CARA_API int cara_set_device(int device);
  *   epi = CARA_EPI_GELU : with u = the bf16-rounded pre-activation: out2 = GELU(u) (exact-erf form, cara.py:84);
  *                         out (NULL for inference) = gelu'(u), kept for backward instead of u
  *   epi = CARA_EPI_DGELU: out = (.) * aux[M,N]          (dX through the fc1 activation: aux = the saved gelu'(u))
+ *   epi = CARA_EPI_DELTA: the dX GEMM of the attention OUTPUT projection (out = dO, head dim 64 = one epilogue step)
+ *                         also emits the softmax-backward row term the attention backward needs,
+ *                         delta[b, h, n] = sum_d bf16(dO)[m, 64h + d] * (aux + aux2)[m, 64h + d],  m = b * seq_n + n,
+ *                         with aux / aux2 = the attention output O as its bf16 (hi, lo) pair (cara_attn_fwd's o, o_lo;
+ *                         32-byte aligned rows) -- the separate pass over dO and O that cara_attn_bwd otherwise runs
+ *                         (autograd of cara.py:47-48) disappears.  N % 64 == 0, M % seq_n == 0.
  * Requirements: K0 % 8 == 0, N % 64 == 0, K1 % 16 == 0, 16-byte aligned bases and row pitches.
  *
  * Side tiles (side != 0): the low-rank operand A1 is itself a contraction of the SAME A0 rows with a [K0, R] factor
@@ -74,6 +80,8 @@ typedef struct cara_gemm_desc {
   void* side_U; long side_ldu;
   float* side_dc;
   void* sync_ws;
+  const void* aux2; int ldaux2; /* CARA_EPI_DELTA */
+  float* delta; int seq_n;      /* CARA_EPI_DELTA: fp32 [M / seq_n, N / 64, seq_n] */
 } cara_gemm_desc;
 CARA_API int cara_gemm_cp(const cara_gemm_desc* d, void* stream);
 
@@ -120,7 +128,9 @@ CARA_API int cara_adapter_cols(const void* X, long ldx, int M, int Kc, const voi
  * D in {64,80}. */
 CARA_API int cara_attn_fwd(const void* qkv, void* o, void* o_lo, float* lse, int B, int N, int H, int D,
                            float scale, void* stream);
-/* delta_ws: caller-provided fp32 workspace [B,H,N] (rowsum(dO (.) O), written by a streaming pre-pass). */
+/* delta_ws: caller-provided fp32 workspace [B,H,N] (rowsum(dO (.) O), written by a streaming pre-pass).
+ * o == NULL (D = 64, N <= 256 only): delta_ws already holds it -- written by the output projection's dX GEMM
+ * (cara_gemm_cp, epi = CARA_EPI_DELTA) -- and the pre-pass is skipped. */
 CARA_API int cara_attn_bwd(const void* qkv, const void* o, const void* o_lo, const float* lse, const void* d_o,
                            void* dqkv, float* delta_ws, int B, int N, int H, int D, float scale, void* stream);
 /* Profiling aid: copies up to n device-side cycle stamps recorded by the attention kernels (debug builds of the

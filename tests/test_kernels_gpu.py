@@ -338,6 +338,36 @@ def test_attention_fwd_bwd(K, B, N, H, D):
         assert rel(dqkv[:, :, i].float(), dref[:, :, i]) < 1.2e-2, name
 
 
+@pytest.mark.parametrize("B,N,H,R", [(3, 197, 12, 16), (256, 197, 12, 16), (5, 50, 4, 0), (2, 256, 16, 32)])
+def test_gemm_delta_epilogue_feeds_attention_backward(K, B, N, H, R):
+    """EPI_DELTA: the output projection's dX GEMM (frozen W^T + adapter-transpose segment) also writes
+    delta[b,h,n] = sum_d bf16(dO) (O_hi + O_lo) -- bit-for-bit the dO it stores, so it must equal the stand-alone
+    pre-pass of cara_attn_bwd to fp32 summation order, and the attention backward fed with it must equal the
+    backward that runs its own pre-pass (autograd of cara.py:44-58)."""
+    from cara_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(11)
+    D = 64
+    C, M = H * D, B * N
+    G = (torch.randn(M, C, device="cuda", generator=g) * 0.5).to(BF16)
+    Wt = (torch.randn(C, C, device="cuda", generator=g) * 0.03).to(BF16)
+    qkv = torch.randn(B, N, 3, H, D, device="cuda", generator=g).to(BF16)
+    o, o_lo, lse = K.attn_fwd(qkv.view(-1), B, N, H, D, D ** -0.5)
+    a1 = b1 = None
+    if R:
+        a1 = (torch.randn(M, 3 * R, device="cuda", generator=g) * 0.3).to(BF16)
+        b1 = (torch.randn(C, 3 * R, device="cuda", generator=g) * 0.1).to(BF16)
+    delta = torch.full((B, H, N), float("nan"), device="cuda")
+    d_o = K.gemm_cp(G, Wt, a1=a1, b1=b1, epi=L.EPI_DELTA, delta=(o, o_lo, delta, N))
+    plain = K.gemm_cp(G, Wt, a1=a1, b1=b1)
+    assert torch.equal(d_o, plain)                                  # the extra epilogue work never touches the output
+    ref = (d_o.float() * (o.float() + o_lo.float())).view(B, N, H, D).sum(-1).permute(0, 2, 1)
+    assert torch.isfinite(delta).all()
+    assert float((delta - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    mine = K.attn_bwd(qkv.view(-1), None, None, lse, d_o, B, N, H, D, D ** -0.5, delta=delta)
+    theirs = K.attn_bwd(qkv.view(-1), o, o_lo, lse, d_o, B, N, H, D, D ** -0.5)
+    assert rel(mine.float(), theirs.float()) < 1e-3                # fp32 summation order of delta -> a few bf16 roundings flip
+
+
 def test_patch_embed_path(K):
     B, S, P, C = 3, 224, 16, 768
     g = torch.Generator(device="cuda").manual_seed(7)
