@@ -60,6 +60,11 @@ _SIGS = {
     "cara_gemm_cp": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "cara_ln_fwd": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "cara_ln_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "cara_ln_rows_supported": (C.c_int, [C.c_int, C.c_int]),
+    "cara_ln_fwd_rows": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float,
+                                   _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "cara_ln_bwd_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                   _P, _P, C.c_int, _P, _P, _P, _P]),
     "cara_adapter_rows_fwd": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "cara_adapter_rows_bwd": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "cara_adapter_cols": (C.c_int, [_P, C.c_long, C.c_int, C.c_int, _P, C.c_long, C.c_int, C.c_int, _P, _P, _P]),

@@ -74,6 +74,28 @@ int cara_ln_bwd(const void* dh, const float* x, const float* mean, const float* 
                     rows_per_sample > 0 ? rows_per_sample : 1, M, C, act_fp32};
   CARA_RET(cara::ln_bwd_launch(a, CARA_STREAM(stream)), "cara_ln_bwd");
 }
+int cara_ln_rows_supported(int C, int Rp) { return cara::ln_rows_supported(C, Rp); }
+int cara_ln_fwd_rows(const float* x_in, const void* delta, const float* rowscale, int rows_per_sample, float* x_out,
+                     const float* gamma, const float* beta, void* h, float* mean, float* rstd, int M, int C, float eps,
+                     const void* At2, const float* scales, int slices, int Rp, float* T, void* Uhat, void* stream) {
+  cara::LnFwdArgs a{x_in, delta, rowscale, rows_per_sample > 0 ? rows_per_sample : 1, x_out, gamma, beta, h, mean,
+                    rstd, M, C, eps, 0};
+  const int rc = cara::ln_fwd_rows_launch(a, static_cast<const bf16*>(At2), scales, slices, Rp, T, static_cast<bf16*>(Uhat),
+                                          CARA_STREAM(stream));
+  if (rc == 1) return fail(-22, "cara_ln_fwd_rows: (C, Rp) not covered, see cara_ln_rows_supported");
+  CARA_RET(rc, "cara_ln_fwd_rows");
+}
+int cara_ln_bwd_rows(const void* dh, const float* x, const float* mean, const float* rstd, const float* gamma,
+                     const float* dx_in, float* dx_out, void* g_out, const float* rowscale, int rows_per_sample, int M,
+                     int C, const void* Bt2, const float* scales, int Rp, const float* T, void* dThat, float* dscales,
+                     void* stream) {
+  cara::LnBwdArgs a{dh, x, mean, rstd, gamma, dx_in, dx_out, g_out, rowscale,
+                    rows_per_sample > 0 ? rows_per_sample : 1, M, C, 0};
+  const int rc = cara::ln_bwd_rows_launch(a, static_cast<const bf16*>(Bt2), scales, Rp, T, static_cast<bf16*>(dThat), dscales,
+                                          CARA_STREAM(stream));
+  if (rc == 1) return fail(-22, "cara_ln_bwd_rows: (C, Rp) not covered, see cara_ln_rows_supported");
+  CARA_RET(rc, "cara_ln_bwd_rows");
+}
 int cara_adapter_rows_fwd(const void* X, long ldx, int M, int K, const void* At, const float* scales, int slices,
                           int Rp, float* T, void* Uhat, void* stream) {
   cara::RowsArgs a{};

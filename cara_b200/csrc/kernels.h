@@ -52,6 +52,13 @@ struct LnBwdArgs {
 };
 int ln_fwd_launch(const LnFwdArgs& a, cudaStream_t st);
 int ln_bwd_launch(const LnBwdArgs& a, cudaStream_t st);
+// ln_rows.cu: the same LayerNorms fused with the rank-R row contraction of the projection they feed (bf16 only).
+// 0 = launched, 1 = (C, Rp) not covered, < 0 = error.
+int ln_rows_supported(int C, int rp);
+int ln_fwd_rows_launch(const LnFwdArgs& l, const __nv_bfloat16* Ft, const float* scales, int slices, int rp, float* T,
+                       __nv_bfloat16* U, cudaStream_t st);
+int ln_bwd_rows_launch(const LnBwdArgs& l, const __nv_bfloat16* Ft, const float* scales, int rp, const float* T,
+                       __nv_bfloat16* dT, float* dc, cudaStream_t st);
 
 // Tall-skinny adapter contractions (skinny.cu)
 struct RowsArgs {

@@ -169,6 +169,56 @@ def ln_bwd(dh, x, mean, rstd, gamma, dx_in=None, rowscale=None, rows_per_sample=
     return dx_out, g_out
 
 
+# the K = C row contractions inside the LayerNorm kernels that produce their operand (csrc/ln_rows.cu).
+# CARA_LN_ROWS: bit 0 = forward (T = h A for qkv / fc1), bit 1 = backward (dU = G B for proj / fc2); 0 = stand-alone passes
+ln_rows = int(__import__("os").environ.get("CARA_LN_ROWS", "3"))
+
+
+def ln_rows_fusable(Cc, Rp, backward=False):
+    return bool(ln_rows & (2 if backward else 1)) and bool(L.lib().cara_ln_rows_supported(int(Cc), int(Rp)))
+
+
+def ln_fwd_rows(x, gamma, beta, a_t2, scales, delta=None, rowscale=None, rows_per_sample=1, eps=1e-6, want_T=True):
+    """``ln_fwd`` (bf16 activations) that also contracts the rows it emits with the consumer's in-side factor:
+    returns (x_out, h, mean, rstd, T fp32 [M,Rp] or None, Uhat bf16 [M,S*3Rp]) -- see cara_ln_fwd_rows."""
+    st = _prep(x)
+    M, Cc = x.shape
+    S, Rp = scales.shape
+    assert x.dtype == F32 and x.is_contiguous() and a_t2.shape == (2 * Rp, Cc) and a_t2.is_contiguous()
+    assert scales.dtype == F32 and scales.is_contiguous()
+    if delta is not None:
+        assert delta.shape == x.shape and delta.dtype == BF16 and delta.is_contiguous()
+    x_out = torch.empty_like(x) if delta is not None else x
+    h = torch.empty((M, Cc), device=x.device, dtype=BF16)
+    mean = torch.empty(M, device=x.device, dtype=F32)
+    rstd = torch.empty(M, device=x.device, dtype=F32)
+    T = torch.empty((M, Rp), device=x.device, dtype=F32) if want_T else None
+    U = torch.empty((M, S * 3 * Rp), device=x.device, dtype=BF16)
+    L.check(L.lib().cara_ln_fwd_rows(x.data_ptr(), _p(delta), _p(rowscale), rows_per_sample,
+                                     _p(x_out) if delta is not None else None, gamma.data_ptr(), beta.data_ptr(),
+                                     h.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, Cc, eps, a_t2.data_ptr(),
+                                     scales.data_ptr(), S, Rp, _p(T), U.data_ptr(), st), "cara_ln_fwd_rows")
+    return x_out, h, mean, rstd, T, U
+
+
+def ln_bwd_rows(dh, x, mean, rstd, gamma, b_t2, scales, T, dsc, dx_in=None, rowscale=None, rows_per_sample=1):
+    """``ln_bwd`` with g_out that also contracts g_out with the out-side factor of the projection it is the gradient
+    of: returns (dx_out, g_out, dThat bf16 [M,3Rp]); dsc fp32 [1,Rp] is accumulated into -- see cara_ln_bwd_rows."""
+    st = _prep(x)
+    M, Cc = x.shape
+    S, Rp = scales.shape
+    assert S == 1 and b_t2.shape == (2 * Rp, Cc) and b_t2.is_contiguous() and T.shape == (M, Rp) and T.is_contiguous()
+    assert dh.dtype == BF16 and dh.is_contiguous() and dsc.dtype == F32 and dsc.numel() == Rp and dsc.is_contiguous()
+    dx_out = torch.empty_like(x)
+    g_out = torch.empty((M, Cc), device=x.device, dtype=BF16)
+    dT = torch.empty((M, 3 * Rp), device=x.device, dtype=BF16)
+    L.check(L.lib().cara_ln_bwd_rows(dh.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                     _p(dx_in), dx_out.data_ptr(), g_out.data_ptr(), _p(rowscale), rows_per_sample, M, Cc,
+                                     b_t2.data_ptr(), scales.data_ptr(), Rp, T.data_ptr(), dT.data_ptr(), dsc.data_ptr(),
+                                     st), "cara_ln_bwd_rows")
+    return dx_out, g_out, dT
+
+
 def factor_operands(F, Rp):
     """fp32 factor [..., rows, R] -> (ext bf16 [..., rows, 3Rp] = [hi|hi|lo], t2 bf16 [..., 2Rp, rows] = [hi^T; lo^T])."""
     F = F.detach().float().contiguous()

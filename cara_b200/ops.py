@@ -100,12 +100,31 @@ class GradSink:
         return self.t["dA%d" % kind][..., :R], self.t["dcs%d" % kind][..., :R], self.t["dB%d" % kind][..., :R], db
 
 
-def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True, train=True):
+class RowsLink:
+    """Hand-over between a LayerNorm kernel and the adapted projection next to it (csrc/ln_rows.cu).
+    Forward link (LayerNorm -> the qkv / fc1 it feeds): ``ops`` = that projection's operands, set by the caller; the
+    LayerNorm deposits ``T`` / ``U`` and the projection skips its rows pass.
+    Backward link (proj / fc2 -> the LayerNorm that adds its output to the residual stream): the projection's forward
+    deposits ``ops``, its saved ``T`` and the ``dcs`` accumulator; the LayerNorm's backward -- whose g_out IS that
+    projection's incoming gradient -- deposits ``dT`` and the projection's backward skips its rows pass."""
+
+    __slots__ = ("ops", "want_T", "T", "U", "dT", "dcs")
+
+    def __init__(self, ops=None, want_T=True):
+        self.ops, self.want_T = ops, want_T        # want_T: keep T for a backward (autograd is off inside Function.forward)
+        self.T = self.U = self.dT = self.dcs = None
+
+
+def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True, train=True, pre=None):
     """The frozen product + the adapter segment (cara.py:35,57,81,92 without the delta weight).  The rank-R row
-    contraction T = x A, Uhat_s = cs_s (.) T that feeds the segment runs as its own pass (default) or, with
-    CARA_SIDE_TILES=1, as side tiles of the same GEMM launch."""
+    contraction T = x A, Uhat_s = cs_s (.) T that feeds the segment comes from the LayerNorm kernel that produced x
+    (``pre``, a filled forward RowsLink), or runs as its own pass (default) or, with CARA_SIDE_TILES=1, as side tiles
+    of the same GEMM launch."""
     T = U = None
-    if ops is not None and not (K.side_tiles and epi == L.EPI_NONE):
+    if ops is not None and pre is not None and pre.U is not None:
+        T, U = pre.T, pre.U
+        y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_ext, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
+    elif ops is not None and not (K.side_tiles and epi == L.EPI_NONE):
         # default: the row contraction T = x A, Uhat_s = cs_s (.) T as its own HBM-bound pass, then the GEMM
         T, U = K.adapter_rows_fwd(x, ops.a_t2, ops.cs_pad)
         y = K.gemm_cp(x, fz.w, bias=bias_eff, a1=U, b1=ops.b_ext, ext_slices=ops.slices, epi=epi, want_pre=want_pre)
@@ -121,7 +140,7 @@ def _cp_linear_fwd(x, fz, bias_eff, ops, epi=L.EPI_NONE, want_pre=True, train=Tr
     return y, T, U
 
 
-def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink=None, delta=None):
+def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink=None, delta=None, dT_pre=None):
     """Returns (dx, dA, dcs, dB, dbias).  ``sink`` = (GradSink, kind, layer): accumulate the factor gradients
     there and hand them to autograd once per projection kind (see GradSink).  ``delta`` (output projection of the
     attention branch only) = (o, o_lo, delta_out, seq_n): the dX GEMM's epilogue also emits rowsum(dX (.) O)."""
@@ -141,9 +160,10 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink
         zs = torch.split(z, sizes)
         dcs, dA, dB = zs[0].view(S, Rp), zs[1].view(Kin, Rp), zs[2].view(w, Rp)
         colsum = zs[3] if need_bias else None
-    if not (K.side_tiles and epi == L.EPI_NONE):
+    if dT_pre is not None or not (K.side_tiles and epi == L.EPI_NONE):
         # the three readers of G run back to back: for the C-wide projections G (77 MB at ViT-B) stays in the 126 MB L2
-        dT, _ = K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)
+        # (dT_pre: dThat and dcs already came out of the LayerNorm backward that produced G)
+        dT = dT_pre if dT_pre is not None else K.adapter_rows_bwd(G, ops.b_t2, ops.cs_pad, T, dsc=dcs)[0]
         K.adapter_cols(G, U, S, Rp, want_colsum=need_bias, out=dB, cs=colsum)
         dx = K.gemm_cp(G, fz.wt, a1=dT, b1=ops.a_ext, ext_slices=1, epi=epi, aux=dgelu_aux, delta=delta) if need_dx else None
         K.adapter_cols(x, dT, 1, Rp, out=dA)
@@ -165,21 +185,38 @@ def _cp_linear_bwd(G, x, fz, ops, T, U, need_dx, need_bias, dgelu_aux=None, sink
     return dx, dA[:, :R], dcs[:, :R], dB[:, :R], colsum
 
 
+def _arm_backward_link(post, ops, T, sink, train):
+    """Forward of proj / fc2: let the LayerNorm backward that will produce this projection's incoming gradient also
+    run its dU = G B contraction (needs the gradient sink: dcs is accumulated in place)."""
+    if post is not None and train and ops is not None and sink is not None and T is not None and ops.slices == 1:
+        post.ops, post.T = ops, T
+        post.dcs = sink[0].t["dcs%d" % sink[1]][sink[2]]
+
+
+def _take_dT(post):
+    if post is None:
+        return None
+    dT, post.dT, post.T, post.ops, post.dcs = post.dT, None, None, None, None
+    return dT
+
+
 class CPLinearFunction(torch.autograd.Function):
     """One CP-adapted frozen projection (qkv: cara.py:25-42, proj: cara.py:50-58)."""
 
     @staticmethod
-    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops, sink=None, link=None):
+    def forward(ctx, x, A, cs, Bf, bias_eff, fz, ops, sink=None, link=None, pre=None, post=None):
         """Without ``sink``: A [K,R], cs [S,R], Bf [N/S,R], bias_eff [N] are this layer's terms.  With ``sink`` =
         (GradSink, kind, layer): cs [L,S,R] and bias_eff [L,N] (and A [L,4C,R] for fc2) are the stacked terms of
         all layers -- autograd sees one gradient per kind instead of one per layer.  ``link`` (an ``AttnLink``, output
         projection only): x is the attention core's output and this backward's dX GEMM also writes the core's
         softmax-backward row term (EPI_DELTA)."""
         bias = bias_eff if (bias_eff is None or sink is None) else bias_eff[sink[2]]
-        y, T, U = _cp_linear_fwd(x, fz, bias if bias is not None else fz.bias, ops, train=any(ctx.needs_input_grad))
-        if sink is not None and any(ctx.needs_input_grad):
+        train = any(ctx.needs_input_grad)
+        y, T, U = _cp_linear_fwd(x, fz, bias if bias is not None else fz.bias, ops, train=train, pre=pre)
+        if sink is not None and train:
             sink[0].pending[sink[1]] += 1
-        ctx.fz, ctx.ops, ctx.sink, ctx.link = fz, ops, sink, link
+        _arm_backward_link(post, ops, T, sink, train)
+        ctx.fz, ctx.ops, ctx.sink, ctx.link, ctx.post = fz, ops, sink, link, post
         ctx.save_for_backward(x, T, U)
         return y
 
@@ -192,8 +229,8 @@ class CPLinearFunction(torch.autograd.Function):
             link.delta = torch.empty(link.shape, device=G.device, dtype=F32)
             delta = (x, link.o_lo, link.delta, link.shape[2])
         dx, dA, dcs, dB, dbias = _cp_linear_bwd(G.contiguous(), x, ctx.fz, ctx.ops, T, U, ni[0], ni[4], sink=ctx.sink,
-                                                delta=delta)
-        return dx, dA, dcs, dB, dbias, None, None, None, None
+                                                delta=delta, dT_pre=_take_dT(ctx.post))
+        return dx, dA, dcs, dB, dbias, None, None, None, None, None, None
 
 
 class CPMlpFunction(torch.autograd.Function):
@@ -202,7 +239,8 @@ class CPMlpFunction(torch.autograd.Function):
     the fc2 dX GEMM epilogue only multiplies by it)."""
 
     @staticmethod
-    def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, fz1, ops1, fz2, ops2, sink1=None, sink2=None):
+    def forward(ctx, x, A1, cs1, B1, bias1, A2, cs2, B2, bias2, fz1, ops1, fz2, ops2, sink1=None, sink2=None,
+                pre=None, post=None):
         train = any(ctx.needs_input_grad)
         if sink1 is not None:                 # stacked terms of all layers (see CPLinearFunction.forward)
             bias1 = None if bias1 is None else bias1[sink1[2]]
@@ -212,8 +250,10 @@ class CPMlpFunction(torch.autograd.Function):
                 sink2[0].pending[sink2[1]] += 1
         # gp = gelu'(u), g = GELU(u) from the fc1 epilogue (u = fc1 pre-activation, never stored)
         (gp, g), T1, U1 = _cp_linear_fwd(x, fz1, bias1 if bias1 is not None else fz1.bias, ops1, epi=L.EPI_GELU,
-                                         want_pre=train, train=train)
+                                         want_pre=train, train=train, pre=pre)
         y, T2, U2 = _cp_linear_fwd(g, fz2, bias2 if bias2 is not None else fz2.bias, ops2, train=train)
+        _arm_backward_link(post, ops2, T2, sink2, train)
+        ctx.post = post
         ctx.fz1, ctx.ops1, ctx.fz2, ctx.ops2 = fz1, ops1, fz2, ops2
         ctx.sink1, ctx.sink2 = sink1, sink2
         ctx.save_for_backward(x, gp, g, T1, U1, T2, U2)
@@ -224,9 +264,9 @@ class CPMlpFunction(torch.autograd.Function):
         x, gp, g, T1, U1, T2, U2 = ctx.saved_tensors
         ni = ctx.needs_input_grad
         du, dA2, dcs2, dB2, db2 = _cp_linear_bwd(G.contiguous(), g, ctx.fz2, ctx.ops2, T2, U2, True, ni[8],
-                                                 dgelu_aux=gp, sink=ctx.sink2)
+                                                 dgelu_aux=gp, sink=ctx.sink2, dT_pre=_take_dT(ctx.post))
         dx, dA1, dcs1, dB1, db1 = _cp_linear_bwd(du, x, ctx.fz1, ctx.ops1, T1, U1, ni[0], ni[4], sink=ctx.sink1)
-        return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None, None, None
+        return dx, dA1, dcs1, dB1, db1, dA2, dcs2, dB2, db2, None, None, None, None, None, None, None, None
 
 
 class AttnLink:
@@ -269,8 +309,13 @@ class LayerNormFunction(torch.autograd.Function):
     """h = LN(x) for the first block / final norm (frozen affine).  x fp32 [M,C]."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, act_dtype):
-        _, h, mean, rstd = K.ln_fwd(x, gamma, beta, eps=eps, act_dtype=act_dtype)
+    def forward(ctx, x, gamma, beta, eps, act_dtype, fl=None):
+        """``fl``: forward RowsLink of the projection that consumes h (its row contraction runs in this kernel)."""
+        if fl is not None and act_dtype == BF16:
+            _, h, mean, rstd, fl.T, fl.U = K.ln_fwd_rows(x, gamma, beta, fl.ops.a_t2, fl.ops.cs_pad, eps=eps,
+                                                         want_T=fl.want_T)
+        else:
+            _, h, mean, rstd = K.ln_fwd(x, gamma, beta, eps=eps, act_dtype=act_dtype)
         ctx.save_for_backward(x, mean, rstd, gamma)
         return h
 
@@ -278,7 +323,7 @@ class LayerNormFunction(torch.autograd.Function):
     def backward(ctx, dh):
         x, mean, rstd, gamma = ctx.saved_tensors
         dx, _ = K.ln_bwd(dh.contiguous(), x, mean, rstd, gamma)
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class AddLayerNormFunction(torch.autograd.Function):
@@ -286,10 +331,17 @@ class AddLayerNormFunction(torch.autograd.Function):
     ``x + drop_path(f(norm(x)))`` re-associated so the add rides in the next LayerNorm's pass."""
 
     @staticmethod
-    def forward(ctx, x, delta, rowscale, gamma, beta, eps, rows_per_sample):
-        x_new, h, mean, rstd = K.ln_fwd(x, gamma, beta, delta=delta, rowscale=rowscale,
-                                        rows_per_sample=rows_per_sample, eps=eps, act_dtype=delta.dtype)
-        ctx.rps = rows_per_sample
+    def forward(ctx, x, delta, rowscale, gamma, beta, eps, rows_per_sample, fl=None, bl=None):
+        """``fl``: forward RowsLink of the projection that consumes h; ``bl``: backward RowsLink armed by the
+        projection that produced ``delta`` (this backward's g is its incoming gradient)."""
+        if fl is not None and delta.dtype == BF16:
+            x_new, h, mean, rstd, fl.T, fl.U = K.ln_fwd_rows(x, gamma, beta, fl.ops.a_t2, fl.ops.cs_pad, delta=delta,
+                                                             rowscale=rowscale, rows_per_sample=rows_per_sample, eps=eps,
+                                                             want_T=fl.want_T)
+        else:
+            x_new, h, mean, rstd = K.ln_fwd(x, gamma, beta, delta=delta, rowscale=rowscale,
+                                            rows_per_sample=rows_per_sample, eps=eps, act_dtype=delta.dtype)
+        ctx.rps, ctx.bl = rows_per_sample, bl
         ctx.save_for_backward(x_new, mean, rstd, gamma, rowscale)
         return x_new, h
 
@@ -298,10 +350,15 @@ class AddLayerNormFunction(torch.autograd.Function):
         x_new, mean, rstd, gamma, rowscale = ctx.saved_tensors
         if dh is None:
             dh = torch.zeros(x_new.shape, device=x_new.device, dtype=BF16)
-        dx, g = K.ln_bwd(dh.contiguous(), x_new, mean, rstd, gamma,
-                         dx_in=None if dx_new is None else dx_new.contiguous(), rowscale=rowscale,
-                         rows_per_sample=ctx.rps, want_g=True)
-        return dx, g, None, None, None, None, None
+        bl = ctx.bl
+        dx_in = None if dx_new is None else dx_new.contiguous()
+        if bl is not None and bl.T is not None and dh.dtype == BF16:
+            dx, g, bl.dT = K.ln_bwd_rows(dh.contiguous(), x_new, mean, rstd, gamma, bl.ops.b_t2, bl.ops.cs_pad, bl.T, bl.dcs,
+                                         dx_in=dx_in, rowscale=rowscale, rows_per_sample=ctx.rps)
+        else:
+            dx, g = K.ln_bwd(dh.contiguous(), x_new, mean, rstd, gamma, dx_in=dx_in, rowscale=rowscale,
+                             rows_per_sample=ctx.rps, want_g=True)
+        return dx, g, None, None, None, None, None, None, None
 
 
 class HeadFunction(torch.autograd.Function):

@@ -96,18 +96,19 @@ def attn_forward(mod, x, staged):
     h, (B, N, C) = _as_act(x)
     H = mod.num_heads
     fq, fp = ops.FrozenLinear.of(mod.qkv), ops.FrozenLinear.of(mod.proj)
+    pre, post = mod.__dict__.pop("_cara_rows", None) or (None, None)     # RowsLinks set by Block.fused_step
     if staged is None:
         qkv = ops.CPLinearFunction.apply(h, None, None, None, None, fq, None)
     else:
         A, cs, Bf, _, sink = staged[0].autograd_args()
-        qkv = ops.CPLinearFunction.apply(h, A, cs, Bf, None, fq, staged[0].ops, sink)
+        qkv = ops.CPLinearFunction.apply(h, A, cs, Bf, None, fq, staged[0].ops, sink, None, pre, None)
     link = ops.AttnLink() if K.attn_delta_fusable(N, C // H) else None
     o = ops.AttnCoreFunction.apply(qkv, B, N, H, C // H, float(mod.scale), link)
     if staged is None:
         y = ops.CPLinearFunction.apply(o, None, None, None, None, fp, None, None, link)
     else:
         A, cs, Bf, bias, sink = staged[1].autograd_args()
-        y = ops.CPLinearFunction.apply(o, A, cs, Bf, bias, fp, staged[1].ops, sink, link)
+        y = ops.CPLinearFunction.apply(o, A, cs, Bf, bias, fp, staged[1].ops, sink, link, None, post)
     y = y.view(B, N, C)
     return y if x.dtype == BF16 else y.to(x.dtype)
 
@@ -123,13 +124,14 @@ def mlp_forward(mod, x, staged):
         return F32M.mlp_forward(mod, x, staged)
     h, (B, N, C) = _as_act(x)
     f1, f2 = ops.FrozenLinear.of(mod.fc1), ops.FrozenLinear.of(mod.fc2)
+    pre, post = mod.__dict__.pop("_cara_rows", None) or (None, None)     # RowsLinks set by Block.fused_step
     if staged is None:
         y = ops.CPMlpFunction.apply(h, None, None, None, None, None, None, None, None, f1, None, f2, None)
     else:
         u, d = staged
         a1, c1, b1, bi1, s1 = u.autograd_args()
         a2, c2, b2, bi2, s2 = d.autograd_args()
-        y = ops.CPMlpFunction.apply(h, a1, c1, b1, bi1, a2, c2, b2, bi2, f1, u.ops, f2, d.ops, s1, s2)
+        y = ops.CPMlpFunction.apply(h, a1, c1, b1, bi1, a2, c2, b2, bi2, f1, u.ops, f2, d.ops, s1, s2, pre, post)
     y = y.view(B, N, -1)
     return y if x.dtype == BF16 else y.to(x.dtype)
 
@@ -160,15 +162,27 @@ class Block(nn.Module):
         out = xr + pending[0].float() * (1.0 if pending[1] is None else pending[1].repeat_interleave(N)[:, None])
         return out.view(B, N, C).to(x.dtype)
 
-    def fused_step(self, x, h, B, N):
-        """x fp32 [M,C] residual, h = LN1(x).  Returns (x after the attention add, (mlp branch, rowscale))
-        with the FFN residual add left pending for the next block's LayerNorm kernel."""
+    def fused_step(self, x, h, B, N, links=None):
+        """x fp32 [M,C] residual, h = LN1(x).  Returns (x after the attention add, (mlp branch, rowscale, link))
+        with the FFN residual add left pending for the next block's LayerNorm kernel.  ``links`` (from
+        ``VisionTransformer._rows_links``) = (qkv forward link -- already filled by the LayerNorm that produced h --,
+        fc1 forward link, backward links wanted): the K = C row contractions of the adapter run inside the LayerNorm
+        kernels."""
         C = x.shape[1]
+        q_fl, f_fl, bwd = links if links is not None else (None, None, False)
+        p_bl = ops.RowsLink() if bwd else None                     # proj -> norm2's backward
+        m_bl = ops.RowsLink() if bwd else None                     # fc2 -> the next block's norm1 backward
+        if links is not None:
+            self.attn.__dict__["_cara_rows"] = (q_fl, p_bl)
         a = self.attn(h.view(B, N, C)).reshape(B * N, C)
+        self.attn.__dict__.pop("_cara_rows", None)
         x, h2 = ops.AddLayerNormFunction.apply(x, a, self._rowscale(B, x.device), self.norm2.weight,
-                                               self.norm2.bias, self.norm2.eps, N)
+                                               self.norm2.bias, self.norm2.eps, N, f_fl, p_bl)
+        if links is not None:
+            self.mlp.__dict__["_cara_rows"] = (f_fl, m_bl)
         m = self.mlp(h2.view(B, N, C)).reshape(B * N, C)
-        return x, (m, self._rowscale(B, x.device))
+        self.mlp.__dict__.pop("_cara_rows", None)
+        return x, (m, self._rowscale(B, x.device), m_bl)
 
 
 class PatchEmbed(nn.Module):
@@ -275,13 +289,15 @@ class VisionTransformer(nn.Module):
         self._predraw_droppath(B, x.device)
         pending = None
         for blk in self.blocks:
+            links = self._rows_links(blk)
+            q_fl = links[0] if links is not None else None
             if pending is None:
                 h = ops.LayerNormFunction.apply(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps,
-                                                F32 if F32M.is_fp32(self) else BF16)
+                                                F32 if F32M.is_fp32(self) else BF16, q_fl)
             else:
                 x, h = ops.AddLayerNormFunction.apply(x, pending[0], pending[1], blk.norm1.weight, blk.norm1.bias,
-                                                      blk.norm1.eps, N)
-            x, pending = blk.fused_step(x, h, B, N)
+                                                      blk.norm1.eps, N, q_fl, pending[2])
+            x, pending = blk.fused_step(x, h, B, N, links)
         # only the class-token rows feed the head: finish the last residual add on [B,C]
         xc = x.view(B, N, C)[:, 0]
         if pending is not None:
@@ -289,6 +305,25 @@ class VisionTransformer(nn.Module):
             xc = xc + (d if pending[1] is None else d * pending[1][:, None])
         hc = ops.LayerNormFunction.apply(xc.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps, F32)
         return self.pre_logits(hc)
+
+    def _rows_links(self, blk):
+        """Forward RowsLinks (qkv, fc1) of one block when the CaRA adapter is installed on this model and its K = C
+        row contractions can run inside the LayerNorm kernels (bf16 path, covered (C, Rp), no exact weight dropout)."""
+        if not hasattr(self, "CP_A1") or F32M.is_fp32(self) or not hasattr(blk.attn, "attn_idx"):
+            return None
+        from . import staging, wdrop
+        if wdrop.wants_exact(self, blk.attn) or wdrop.wants_exact(self, blk.mlp):
+            return None
+        amap, mmap = staging.staged(self)
+        ta, tm = amap.get(id(blk.attn)), mmap.get(id(blk.mlp))
+        if ta is None or tm is None or ta[0].ops is None or tm[0].ops is None:
+            return None
+        rp = ta[0].ops.rp
+        fwd, bwd = K.ln_rows_fusable(self.embed_dim, rp), K.ln_rows_fusable(self.embed_dim, rp, backward=True)
+        if not (fwd or bwd):
+            return None
+        train = torch.is_grad_enabled()
+        return (ops.RowsLink(ta[0].ops, train) if fwd else None, ops.RowsLink(tm[0].ops, train) if fwd else None, bwd)
 
     def _predraw_droppath(self, B, device):
         """Stochastic depth draws two per-sample multipliers per block (timm drop_path); draw all of them with

@@ -99,6 +99,25 @@ CARA_API int cara_ln_bwd(const void* dh, const float* x, const float* mean, cons
                          const float* dx_in, float* dx_out, void* g_out, const float* rowscale, int rows_per_sample,
                          int M, int C, int act_fp32, void* stream);
 
+/* The two LayerNorms above fused with the rank-R row contraction of the projection they feed (bf16 activations):
+ * the rows a LayerNorm CTA emits stay in shared memory and are contracted with the (hi, lo) factor there, so the
+ * stand-alone pass over the same [M, C] matrix (cara_adapter_rows_fwd / _bwd with K = C resp. N = C, slices = 1) and
+ * its launch disappear.  Replaces, besides the LayerNorm, the `x @ A` half of cara.py:35 (qkv, after norm1) and :81
+ * (fc1, after norm2), and autograd's `G @ B` for :57 (proj; G = the g_out of norm2's backward) and :92 (fc2; G = the
+ * g_out of the next block's norm1 backward).  Operands and outputs exactly as in cara_adapter_rows_fwd / _bwd:
+ *   forward : T = h At2^T (fp32 [M,Rp], may be NULL), Uhat[:, s*3Rp:(s+1)*3Rp] = split(scales[s] (.) T), s < slices
+ *   backward: dU = g_out Bt2^T, dThat = split(scales[0] (.) dU) (bf16 [M,3Rp]), dscales[0..Rp) += sum_m dU (.) T
+ * cara_ln_rows_supported(C, Rp) != 0 for the shapes that keep >= 2 CTAs per SM: (768, 16), (1024, 16). */
+CARA_API int cara_ln_rows_supported(int C, int Rp);
+CARA_API int cara_ln_fwd_rows(const float* x_in, const void* delta, const float* rowscale, int rows_per_sample,
+                              float* x_out, const float* gamma, const float* beta, void* h, float* mean, float* rstd,
+                              int M, int C, float eps, const void* At2, const float* scales, int slices, int Rp,
+                              float* T, void* Uhat, void* stream);
+CARA_API int cara_ln_bwd_rows(const void* dh, const float* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* dx_in, float* dx_out, void* g_out, const float* rowscale,
+                              int rows_per_sample, int M, int C, const void* Bt2, const float* scales, int Rp,
+                              const float* T, void* dThat, float* dscales, void* stream);
+
 /* Rank-R side chain.  Precision convention: factor matrices and low-rank activations are bf16 (hi, lo) pairs
  * (x = hi + lo).  A transposed factor operand "Ft2" is bf16 [2*Rp, K] = [hi rows ; lo rows]; a low-rank
  * activation block is bf16 [.., 3*Rp] = [hi | lo | hi], to be multiplied in cara_gemm_cp (K1 = 3*Rp) against

@@ -164,6 +164,52 @@ def _rand_split(shape, g, scale=1.0):
     return hi.float() + lo.float(), torch.cat([hi, lo, hi], -1)
 
 
+@pytest.mark.parametrize("M,C,R,S", [(197 * 3 + 5, 768, 16, 3), (50432, 768, 16, 4), (1000, 768, 8, 1), (333, 1024, 12, 4)])
+def test_layernorm_with_fused_row_contraction(K, M, C, R, S):
+    """cara_ln_fwd_rows / cara_ln_bwd_rows = the plain LayerNorm kernels + the stand-alone rows pass on the rows they
+    emit: LayerNorm outputs bit-identical, T / Uhat / dThat / dcs equal up to fp32 summation order."""
+    rps = 197
+    g = torch.Generator(device="cuda").manual_seed(21)
+    Rp = K.round_rank(R)
+    assert K.ln_rows_fusable(C, Rp) and K.ln_rows_fusable(C, Rp, backward=True)
+    x = torch.randn(M, C, device="cuda", generator=g) * 2 + 0.3
+    delta = torch.randn(M, C, device="cuda", generator=g).to(BF16)
+    rs = torch.rand((M + rps - 1) // rps, device="cuda", generator=g) + 0.5
+    gamma = torch.randn(C, device="cuda", generator=g) * 0.1 + 1
+    beta = torch.randn(C, device="cuda", generator=g) * 0.1
+    A = torch.randn(C, R, device="cuda", generator=g) * 0.1
+    _, a_t2 = K.factor_operands(A, Rp)
+    cs = torch.nn.functional.pad(torch.randn(S, R, device="cuda", generator=g), (0, Rp - R)).contiguous()
+    for with_delta in (True, False):
+        kw = dict(delta=delta, rowscale=rs, rows_per_sample=rps) if with_delta else {}
+        x0, h0, mean0, rstd0 = K.ln_fwd(x, gamma, beta, act_dtype=BF16, **kw)
+        T0, U0 = K.adapter_rows_fwd(h0, a_t2, cs)
+        x1, h1, mean1, rstd1, T1, U1 = K.ln_fwd_rows(x, gamma, beta, a_t2, cs, **kw)
+        assert torch.equal(h0, h1) and torch.equal(mean0, mean1) and torch.equal(rstd0, rstd1) and torch.equal(x0, x1)
+        assert rel(T1, T0) < 2e-6
+        assert rel(_unsplit(U1, S, Rp), _unsplit(U0, S, Rp)) < 1e-5
+        assert float(T1[:, R:].abs().max()) == 0.0 if R < Rp else True
+    _, _, _, _, Tn, Un = K.ln_fwd_rows(x, gamma, beta, a_t2, cs, want_T=False)
+    assert Tn is None and torch.equal(Un, U1)
+    # backward: g_out is the gradient of a slices = 1 projection with out-side factor B; T = that projection's saved T
+    Bf = torch.randn(C, R, device="cuda", generator=g) * 0.1
+    _, b_t2 = K.factor_operands(Bf, Rp)
+    cs1 = cs[:1].contiguous()
+    T = torch.nn.functional.pad(torch.randn(M, R, device="cuda", generator=g), (0, Rp - R)).contiguous()
+    dh = torch.randn(M, C, device="cuda", generator=g).to(BF16)
+    dx_in = torch.randn(M, C, device="cuda", generator=g)
+    for with_in in (True, False):
+        kw = dict(dx_in=dx_in if with_in else None, rowscale=rs, rows_per_sample=rps)
+        dx0, g0 = K.ln_bwd(dh, x0, mean0, rstd0, gamma, want_g=True, **kw)
+        dc1 = torch.zeros(1, Rp, device="cuda")
+        dx1, g1, dT1 = K.ln_bwd_rows(dh, x0, mean0, rstd0, gamma, b_t2, cs1, T, dc1, **kw)
+        assert rel(dx1, dx0) < 1e-6 and rel(g1.float(), g0.float()) < 1e-3   # two compilations of the same formulas
+        dT0, dc0 = K.adapter_rows_bwd(g1, b_t2, cs1, T)                       # the stand-alone pass on the same G
+        assert rel(_unsplit(dT1, 1, Rp), _unsplit(dT0, 1, Rp)) < 1e-5
+        assert rel(dc1, dc0) < 1e-4
+
+
+
 @pytest.mark.parametrize("M,Kd,R,S", [(1000, 768, 16, 3), (50432, 768, 16, 4), (333, 3072, 8, 1), (700, 1024, 32, 4)])
 def test_adapter_rows_fwd(K, M, Kd, R, S):
     Rp = K.round_rank(R)
