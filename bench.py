@@ -81,7 +81,7 @@ class ClockSampler:
     """nvidia-smi SM clock / throttle-reason samples taken DURING the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -109,8 +109,18 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        pw = sorted(v for v in (num(r[6]) for r in self.rows if len(r) >= 8) if v is not None)
+        pl = [v for v in (num(r[7]) for r in self.rows if len(r) >= 8) if v is not None]
+        # board power under load next to its limit: with sw_power_cap active the step is bounded by energy, not by the
+        # sum of its kernels' isolated times
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
+                "power_limit_w": max(pl) if pl else None}
 
 
 def build_model(cfg, device):

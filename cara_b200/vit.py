@@ -311,6 +311,8 @@ class VisionTransformer(nn.Module):
         row contractions can run inside the LayerNorm kernels (bf16 path, covered (C, Rp), no exact weight dropout)."""
         if not hasattr(self, "CP_A1") or F32M.is_fp32(self) or not hasattr(blk.attn, "attn_idx"):
             return None
+        if "forward" not in blk.attn.__dict__ or "forward" not in blk.mlp.__dict__:
+            return None                       # un-patched (or merged for --evaluate): the plain forwards take no adapter terms
         from . import staging, wdrop
         if wdrop.wants_exact(self, blk.attn) or wdrop.wants_exact(self, blk.mlp):
             return None

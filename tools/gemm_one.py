@@ -14,7 +14,11 @@ if ext:
     kw = dict(a1=torch.randn(M, S * 48, device="cuda").bfloat16(), b1=torch.randn(N // S, 48, device="cuda").bfloat16(), ext_slices=S)
 if epi == 2:
     kw["aux"] = torch.randn(M, N, device="cuda").bfloat16()
-run = lambda: K.gemm_cp(a, w, bias=b, epi=epi, **kw)
+if epi == 3:   # EPI_DELTA: the output projection's dX GEMM also writes the attention backward's row term
+    kw["delta"] = (torch.randn(M, N, device="cuda").bfloat16(), (torch.randn(M, N, device="cuda") * 0.01).bfloat16(),
+                   torch.empty(M // 197, N // 64, 197, device="cuda"), 197)
+    b = None
+run = lambda: K.gemm_cp(a, w, bias=b, epi=epi, **kw)  # noqa: E731
 for _ in range(3):
     y = run()
 torch.cuda.synchronize()
