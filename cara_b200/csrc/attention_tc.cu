@@ -16,6 +16,7 @@
 #include "ptx.cuh"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace cara {
 namespace {
@@ -203,6 +204,250 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// [r2b] The same forward with EIGHT softmax warps: two per TMEM lane quarter, each taking half of the key columns of its
+// query row.  The softmax (two passes over the row in tensor memory + the exp) is the serial part of a head -- with four
+// warps the CTA spends most of its time there while the tensor pipe waits -- so halving it shortens every tile.
+//   * half 0 owns score columns [0, split), half 1 [split, npad); each packs its probabilities over its OWN consumed
+//     scores ([0, split/2) and [split, split + (npad - split)/2)), so the halves never touch each other's columns and
+//     the P V MMA reads k-step j from column (16j < split ? 8j : split + (16j - split)/2);
+//   * the two partial row maxima (and later the two partial row sums) cross through shared memory with one 64-thread
+//     named barrier per lane quarter;
+//   * the epilogue splits the 64 output columns the same way (32 per thread).
+constexpr int TC8_THREADS = 288;         // warps 0-7: softmax / epilogue (lane quarter = warp & 3, column half = warp >> 2), warp 8: TMA + MMA
+
+// one named barrier per lane quarter (immediate ids, so ptxas reserves 5 barriers per CTA and not all 16)
+__device__ __forceinline__ void pair_sync(int q4) {
+  switch (q4) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+__global__ void __launch_bounds__(TC8_THREADS, 2)
+attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a, const int npad) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tile0 = (raw + 1023u) & ~1023u;
+  const uint32_t tile_bytes = static_cast<uint32_t>(npad) * 128u;
+  const uint32_t sQ = tile0, sK = tile0 + tile_bytes, sV = tile0 + 2u * tile_bytes;
+  const uint32_t span = 3u * tile_bytes > 32768u ? 3u * tile_bytes : 32768u;
+  const uint32_t bars = tile0 + span;
+  const uint32_t bar_qk = bars, bar_v = bars + 8, bar_s = bars + 16, bar_p = bars + 24, bar_o = bars + 32,
+                 bar_od = bars + 40, tmem_slot = bars + 48, xch = bars + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* s_max = reinterpret_cast<float*>(smem_raw + (xch - raw));       // [2 halves][128 rows]
+  float* s_sum = s_max + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, C = a.H * TC_D;
+  const int mtiles = (N + 127) / 128;
+  const int split = ((npad / 16 + 1) / 2) * 16;
+  const int heads = a.B * a.H;                                 // persistent: this CTA takes heads blockIdx.x, + gridDim.x, ...
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_o, 1);
+      mbar_init(bar_od, 256);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<TC_TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // The next head's Q / K are requested the moment this head's last S = Q K^T has retired, its V the moment the
+      // last P V has retired: with two resident CTAs per SM and 78 KB per head, a CTA that only starts loading when it
+      // starts a head leaves the memory system with too little in flight (2.7 TB/s).
+      auto load_qk = [&](int head) {
+        const int row0 = (head / a.H) * N, col = (head % a.H) * TC_D;
+        mbar_expect_tx(bar_qk, 2u * tile_bytes);
+        tma_load_2d(sQ, &map_qkv, bar_qk, col, row0);
+        tma_load_2d(sK, &map_qkv, bar_qk, C + col, row0);
+      };
+      auto load_v = [&](int head) {
+        const int row0 = (head / a.H) * N, col = (head % a.H) * TC_D;
+        mbar_expect_tx(bar_v, tile_bytes);
+        tma_load_2d(sV, &map_qkv, bar_v, 2 * C + col, row0);
+      };
+      const uint32_t idesc_s = umma_idesc_bf16_major(128, npad, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_major(128, TC_D, 0, 1);
+      uint32_t it = 0, n = 0;
+      if (static_cast<int>(blockIdx.x) < heads) {
+        load_qk(blockIdx.x);
+        load_v(blockIdx.x);
+      }
+      for (int head = blockIdx.x; head < heads; head += gridDim.x, ++it) {
+        const int next = head + static_cast<int>(gridDim.x);
+        mbar_wait(bar_qk, it & 1u);
+        for (int i = 0; i < mtiles; ++i, ++n) {
+          if (n > 0) mbar_wait(bar_od, (n - 1u) & 1u);                       // previous O has been read out of TMEM
+          tc_fence_after();
+          const uint64_t dq = umma_desc_sw128(sQ + static_cast<uint32_t>(i) * 16384u);
+          const uint64_t dk = umma_desc_sw128(sK);
+#pragma unroll
+          for (int k = 0; k < TC_D / 16; ++k) umma_bf16(tmem_base, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(bar_s);
+          if (i == mtiles - 1 && next < heads) {                             // Q / K are dead once the last S has retired
+            mbar_wait(bar_s, n & 1u);
+            load_qk(next);
+          }
+          mbar_wait(bar_p, n & 1u);                                          // probabilities are in TMEM
+          tc_fence_after();
+          if (i == 0) mbar_wait(bar_v, it & 1u);
+          for (int k = 0; k < npad / 16; ++k) {
+            const int c = 16 * k;
+            const uint32_t pcol = static_cast<uint32_t>(c < split ? (c >> 1) : split + ((c - split) >> 1));
+            const uint64_t dv = umma_desc_mn_sw128(sV + static_cast<uint32_t>(k) * 2048u, tile_bytes, 1024u);
+            umma_bf16_ts(tmem_base + TC_O_COL, tmem_base + pcol, dv, idesc_o, k != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_o);
+          if (i == mtiles - 1 && next < heads) {                             // V is dead once the last P V has retired
+            mbar_wait(bar_o, n & 1u);
+            load_v(next);
+          }
+        }
+      }
+    }
+  } else {
+    const int q4 = warp & 3, half = warp >> 2;
+    const int t = q4 * 32 + lane;                                  // query row of this thread inside the tile
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    const float sl2 = a.scale * 1.4426950408889634f;
+    const int cb = half == 0 ? 0 : split, ce = half == 0 ? split : npad;
+    uint32_t n = 0;
+    for (int head = blockIdx.x; head < heads; head += gridDim.x) {
+    const int b = head / a.H, h = head % a.H;
+    for (int i = 0; i < mtiles; ++i, ++n) {
+      const int row = i * 128 + t;
+      const bool warp_live = i * 128 + q4 * 32 < N;               // uniform over the two warps of a lane quarter
+      mbar_wait(bar_s, n & 1u);
+      tc_fence_after();
+      float mx = -CUDART_INF_F, l = 0.f;
+      if (warp_live) {
+        // pass 1: maximum over this half's valid keys, then the row maximum through shared memory
+        int c0 = cb;
+        for (; c0 + 32 <= ce; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c0 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
+        }
+        if (c0 < ce) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        s_max[half * 128 + t] = mx;
+        pair_sync(q4);
+        mx = fmaxf(mx, s_max[(half ^ 1) * 128 + t]);               // (half 0 always holds a valid key: finite)
+        // pass 2: p = 2^(s*sl2 - max*sl2), partial row sum, packed bf16 over this half's own consumed scores
+        const float msc = mx * sl2;
+        for (c0 = cb; c0 + 32 <= ce; c0 += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld32(lane_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), sl2, -msc));
+            float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -msc));
+            if (c0 + 2 * j >= N) p0 = 0.f;
+            if (c0 + 2 * j + 1 >= N) p1 = 0.f;
+            l += p0 + p1;
+            pk[j] = pack_bf16(p0, p1);
+          }
+          tmem_st16(lane_addr + cb + ((c0 - cb) >> 1), pk);
+        }
+        if (c0 < ce) {
+          uint32_t r[16], pk[8];
+          tmem_ld16(lane_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), sl2, -msc));
+            float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -msc));
+            if (c0 + 2 * j >= N) p0 = 0.f;
+            if (c0 + 2 * j + 1 >= N) p1 = 0.f;
+            l += p0 + p1;
+            pk[j] = pack_bf16(p0, p1);
+          }
+          tmem_st8(lane_addr + cb + ((c0 - cb) >> 1), pk);
+        }
+        tmem_st_wait();
+        s_sum[half * 128 + t] = l;
+      }
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      mbar_wait(bar_o, n & 1u);
+      tc_fence_after();
+      uint32_t o[32];
+      if (warp_live) {
+        tmem_ld32(lane_addr + TC_O_COL + 32 * half, o);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_od);
+      if (warp_live) {
+        pair_sync(q4);                                             // the partner's partial sum is in shared memory
+        l += s_sum[(half ^ 1) * 128 + t];
+        if (row < N) {
+          const float inv = 1.0f / l;
+          const long off = (static_cast<long>(b) * N + row) * C + h * TC_D + 32 * half;
+          __nv_bfloat16* po = a.o + off;
+          __nv_bfloat16* pl = a.o_lo != nullptr ? a.o_lo + off : nullptr;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v[16];
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(o[16 * j + e]) * inv;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+              const float2 hf = unpack_bf16(hi[e]);
+              lo[e] = pack_bf16(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+            }
+            st_global_v8(po + 16 * j, hi);
+            if (pl != nullptr) st_global_v8(pl + 16 * j, lo);
+          }
+          if (half == 0 && a.lse != nullptr) a.lse[(static_cast<long>(b) * a.H + h) * N + row] = mx * sl2 + log2f(l);
+        }
+      }
+    }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<TC_TMEM_COLS>(tmem_base);
   }
@@ -609,6 +854,27 @@ int attn_fwd_tc_launch(const AttnArgs& a, cudaStream_t st) {
         cudaSuccess)
       return -52;
     configured = true;
+  }
+  // [r2b] eight softmax warps (CARA_ATTN_FWD8=0: the four-warp kernel)
+  static int fwd8 = -1;
+  if (fwd8 < 0) { const char* e = getenv("CARA_ATTN_FWD8"); fwd8 = e != nullptr ? atoi(e) : 1; }
+  if (fwd8) {
+    static bool configured8 = false;
+    if (!configured8) {
+      if (cudaFuncSetAttribute(attn_fwd_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               1024 + 3 * 256 * 128 + 64 + 2048) != cudaSuccess)
+        return -52;
+      configured8 = true;
+    }
+    // persistent: two resident CTAs per SM walk over the (sample, head) pairs (CARA_ATTN_FWD8=2: one CTA per pair)
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int grid = a.B * a.H;
+    if (fwd8 == 1 && grid > 2 * sms) grid = 2 * sms;
+    return launch_pdl_f<2>(attn_fwd_tc8_kernel, dim3(grid), dim3(TC8_THREADS), smem + 2048, st, map, a, npad) == cudaSuccess ? 0 : -53;
   }
   return launch_pdl_f<2>(attn_fwd_tc_kernel, dim3(a.B * a.H), dim3(TC_THREADS), smem, st, map, a, npad) == cudaSuccess ? 0 : -53;
 }

@@ -6,7 +6,7 @@ O=gpurun_out
 NCU="ncu --set full --clock-control none --import-source on -f"
 $NCU -k regex:gemm_cp_kernel -s 7 -c 1 -o $O/r02b_gemm_projdx_delta_N768_K768 python tools/gemm_one.py 50432 768 768 3 1 > $O/ncu_projdx_delta.log 2>&1
 LN_ONCE=1 $NCU -k regex:ln_fwd_rows\|ln_bwd_rows -c 2 -o $O/r02b_ln_rows python tools/ln_rows_time.py > $O/ncu_ln_rows.log 2>&1
-$NCU -k regex:attn_bwd_tc -s 1 -c 1 -o $O/r02b_attn_bwd python tools/attn_one.py > $O/ncu_attn_bwd.log 2>&1
+ATTN_TIME=0 $NCU -k regex:attn_bwd_tc -s 1 -c 1 -o $O/r02b_attn_bwd python tools/attn_one.py > $O/ncu_attn_bwd.log 2>&1
 python tools/ncu_summary.py $O/r02b_gemm_projdx_delta_N768_K768.ncu-rep $O/r02b_ln_rows.ncu-rep $O/r02b_attn_bwd.ncu-rep > $O/r02b_ncu_full_summary.txt 2>&1
 # launch list of the bench command: every launch, the summary takes the last two replayed steps
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02b_launches_all.csv \
