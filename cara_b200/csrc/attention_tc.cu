@@ -374,14 +374,24 @@ attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs 
           uint32_t r[32], pk[16];
           tmem_ld32(lane_addr + c0, r);
           tmem_ld_wait();
+          if (c0 + 32 <= N) {                                      // (only the chunk that straddles N pays for the mask)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), sl2, -msc));
-            float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -msc));
-            if (c0 + 2 * j >= N) p0 = 0.f;
-            if (c0 + 2 * j + 1 >= N) p1 = 0.f;
-            l += p0 + p1;
-            pk[j] = pack_bf16(p0, p1);
+            for (int j = 0; j < 16; ++j) {
+              const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), sl2, -msc));
+              const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -msc));
+              l += p0 + p1;
+              pk[j] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), sl2, -msc));
+              float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -msc));
+              if (c0 + 2 * j >= N) p0 = 0.f;
+              if (c0 + 2 * j + 1 >= N) p1 = 0.f;
+              l += p0 + p1;
+              pk[j] = pack_bf16(p0, p1);
+            }
           }
           tmem_st16(lane_addr + cb + ((c0 - cb) >> 1), pk);
         }
