@@ -118,9 +118,11 @@ class ClockSampler:
         pl = [v for v in (num(r[7]) for r in self.rows if len(r) >= 8) if v is not None]
         # board power under load next to its limit: with sw_power_cap active the step is bounded by energy, not by the
         # sum of its kernels' isolated times
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
-                "power_limit_w": max(pl) if pl else None}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm)}
+        if len(pw) >= 15:      # nvidia-smi's power.draw is a ~1 s running average: only meaningful over a window of seconds
+            out.update({"power_w": pw[len(pw) // 2], "power_limit_w": max(pl) if pl else None})
+        return out
 
 
 def build_model(cfg, device):
