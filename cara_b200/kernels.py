@@ -5,6 +5,7 @@ PyTorch owns the memory and the stream; these functions only pass ``data_ptr()``
 path here by design.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -15,11 +16,11 @@ launch_count = 0  # number of cara_* kernel launches issued (bench.py reports it
 param_generation = 0  # bumped by adamw_step: parameters changed behind autograd's version counters
 # CARA_SIDE_TILES=1: compute the rank-R row contractions (T = x A, dU = g B) as side tiles inside the projection GEMM's
 # launch instead of the stand-alone rows kernel.  Opt-in: correct (tests/test_kernels_gpu.py::test_gemm_side_tiles_*)
-# but measured slower in the step on B200 (profiles/r02_side_tiles.md).
-side_tiles = __import__("os").environ.get("CARA_SIDE_TILES", "0") == "1"
+# and step-neutral on B200 (profiles/r02_side_tiles.md); with the LayerNorm fusion below no stand-alone rows pass is left.
+side_tiles = os.environ.get("CARA_SIDE_TILES", "0") == "1"
 # the attention backward's rowsum(dO (.) O) out of the output projection's dX GEMM epilogue (CARA_DELTA_IN_GEMM=0: the
 # stand-alone pre-pass inside cara_attn_bwd)
-delta_in_gemm = __import__("os").environ.get("CARA_DELTA_IN_GEMM", "1") == "1"
+delta_in_gemm = os.environ.get("CARA_DELTA_IN_GEMM", "1") == "1"
 gemm_events = None  # bench.py: list of (start event, end event, algorithmic flops) per fused-projection launch
 _dev = [None]
 
@@ -171,7 +172,7 @@ def ln_bwd(dh, x, mean, rstd, gamma, dx_in=None, rowscale=None, rows_per_sample=
 
 # the K = C row contractions inside the LayerNorm kernels that produce their operand (csrc/ln_rows.cu).
 # CARA_LN_ROWS: bit 0 = forward (T = h A for qkv / fc1), bit 1 = backward (dU = G B for proj / fc2); 0 = stand-alone passes
-ln_rows = int(__import__("os").environ.get("CARA_LN_ROWS", "3"))
+ln_rows = int(os.environ.get("CARA_LN_ROWS", "3"))
 
 
 def ln_rows_fusable(Cc, Rp, backward=False):
@@ -310,7 +311,7 @@ def attn_fwd(qkv, B, N, H, D, scale, train=True):
 def attn_delta_fusable(N, D):
     """Shapes whose softmax-backward row term the output projection's dX GEMM can emit (EPI_DELTA): the tcgen05
     attention path, head dim = one 64-column epilogue step."""
-    return delta_in_gemm and D == 64 and N <= 256 and (int(__import__("os").environ.get("CARA_ATTN_TC", "3")) & 2) != 0
+    return delta_in_gemm and D == 64 and N <= 256 and (int(os.environ.get("CARA_ATTN_TC", "3")) & 2) != 0
 
 
 def attn_bwd(qkv, o, o_lo, lse, d_o, B, N, H, D, scale, delta=None):
