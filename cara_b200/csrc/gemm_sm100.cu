@@ -337,7 +337,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           // ring slot layout of a side tile: [A0 k-block 2f | A0 k-block 2f+1 | P k-block 2f | P k-block 2f+1]
           // (half as many ring round trips as one k-block per slot: the loop is bound by TMA latency, not bytes)
           for (int f = 0; f < side_fills; ++f) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_wait_park(empty_bar(s), ph ^ 1u);
             const uint32_t sa = tiles + s * STAGE_BYTES;
             const int nsub = p.kblocks_main - 2 * f < 2 ? 1 : 2;
             mbar_expect_tx(full_bar(s), nsub * (A_BYTES + side_n * BK * 2));
@@ -367,7 +367,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);       // stage free
+          mbar_wait_park(empty_bar(s), ph ^ 1u);       // stage free
           const uint32_t sa = tiles + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
@@ -400,16 +400,16 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (ti.kind == TILE_SKIP) continue;
         const bool is_side = ti.kind == TILE_SIDE;
         const int as = acc.cur;
-        mbar_wait(tempty_bar(as), acc.parity(as) ^ 1u);   // the output-tile epilogue has drained this accumulator
+        mbar_wait_park(tempty_bar(as), acc.parity(as) ^ 1u);   // the output-tile epilogue has drained this accumulator
         if (side_undrained) {                     // ... and the side warps the columns the last side tile borrowed
-          mbar_wait(sempty_bar, (side_count - 1u) & 1u);
+          mbar_wait_park(sempty_bar, (side_count - 1u) & 1u);
           side_undrained = false;
         }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
         const int nkb = is_side ? side_fills : kblocks;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_bar(s), ph);             // TMA bytes have landed
+          mbar_wait_park(full_bar(s), ph);             // TMA bytes have landed
           tc_fence_after();
           const uint32_t sa = tiles + s * STAGE_BYTES;
           const uint64_t da = umma_desc_sw128(sa);
@@ -460,7 +460,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const TileInfo ti = decode_tile(t, p.tiles_m, p.tiles_n, side_tiles != 0, p.side_la);
       if (ti.kind == TILE_SKIP) continue;
       if (ti.kind == TILE_MAIN) { cur ^= 1; continue; }
-      mbar_wait(sfull_bar, k & 1u);
+      mbar_wait_park(sfull_bar, k & 1u);
       ++k;
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(cur * BN);
@@ -519,7 +519,7 @@ gemm_cp_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
       };
       if constexpr (EPI == EPI_DELTA) { if (n0 + c_first * EC < p.N) load_o(n0 + c_first * EC); }
-      mbar_wait(tfull_bar(as), acc.parity(as));
+      mbar_wait_park(tfull_bar(as), acc.parity(as));
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
