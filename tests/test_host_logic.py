@@ -297,3 +297,49 @@ def test_create_model_raises_on_missing_checkpoint(tmp_path):
     with pytest.warns(UserWarning):
         create_model("vit_base_patch16_224_in21k", checkpoint_path=missing, allow_missing_checkpoint=True, depth=1,
                      embed_dim=128, num_heads=2)
+
+
+def test_hand_over_links_between_autograd_functions():
+    """The Python side of the fused hand-overs (cara_b200.ops): a backward RowsLink is armed only when the projection
+    trains through the gradient sink with one slice, is consumed exactly once, and the per-block link decision refuses
+    models that cannot use the fused LayerNorm kernels (no CUDA calls here)."""
+    from cara_b200 import ops, vit
+    from src.cara.cara import cara
+
+    class FakeOps:
+        slices, rp = 1, 16
+
+    class FakeSink:
+        def __init__(self):
+            self.t = {"dcs1": torch.zeros(3, 1, 16), "dcs3": torch.zeros(3, 1, 16)}
+
+    T = torch.zeros(5, 16)
+    sink = (FakeSink(), 1, 2)
+    link = ops.RowsLink()
+    ops._arm_backward_link(link, FakeOps(), T, sink, True)
+    assert link.T is T and link.ops is not None and link.dcs.shape == (1, 16)
+    assert link.dcs.data_ptr() == sink[0].t["dcs1"][2].data_ptr()          # the LayerNorm accumulates in place
+    for bad in [dict(train=False), dict(sink=None), dict(T=None)]:
+        l2 = ops.RowsLink()
+        kw = dict(ops=FakeOps(), T=T, sink=sink, train=True)
+        kw.update(bad)
+        ops._arm_backward_link(l2, kw["ops"], kw["T"], kw["sink"], kw["train"])
+        assert l2.T is None and l2.ops is None
+    wide = FakeOps(); wide.slices = 3                                       # qkv / fc1 never get a backward link
+    l3 = ops.RowsLink()
+    ops._arm_backward_link(l3, wide, T, sink, True)
+    assert l3.T is None
+    assert ops._take_dT(None) is None and ops._take_dT(link) is None        # the LayerNorm backward never ran
+    link.dT = torch.ones(5, 48)
+    got = ops._take_dT(link)
+    assert got is not None and link.dT is None and link.T is None and link.dcs is None and ops._take_dT(link) is None
+
+    # per-block decision: un-adapted model -> no links; fp32 parity mode -> no links; merged (forward un-patched) -> none
+    m = vit.create_model("vit_base_patch16_224_in21k", depth=1)
+    assert m._rows_links(m.blocks[0]) is None
+    m = cara({"model": m, "rank": 8, "scale": 1.0, "l_mu": 1.0, "l_std": 0.0})
+    m.__dict__["cara_precision"] = "fp32"
+    assert m._rows_links(m.blocks[0]) is None
+    m.__dict__["cara_precision"] = "bf16"
+    m.blocks[0].attn.__dict__.pop("forward")
+    assert m._rows_links(m.blocks[0]) is None
