@@ -9,7 +9,8 @@
 // that the tcgen05 GEMM's adapter segment computes hi*Bhi + lo*Bhi + hi*Blo against [Bhi | Bhi | Blo].
 //
 // (The row-wise contractions can also run as side tiles INSIDE the tcgen05 projection GEMM -- gemm_sm100.cu, opt-in:
-// measured slower in the step than these stand-alone passes, profiles/r02_side_tiles.md.)
+// measured level with these stand-alone passes in the step, profiles/r02_side_tiles.md; the K = C ones also run inside the
+// LayerNorm kernels, ln_rows.cu, default on.)
 //
 //   rows_kernel (row-wise, K reduced):
 //     fwd : T = X A                     [M,Rp] fp32 (saved),  Uhat_s = cs_s (.) T   [M,S*3Rp] bf16 (hi|lo|hi)
